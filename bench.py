@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""Headline benchmark: proposed-points/sec through MLFriends.inside() + loglike, N_live=4000, d=20.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path)
+
+A step = one pass of the hot path over one batch of synthetic proposals per GPU:
+``mask = region.inside(c); L = loglike(c[mask])``.  Workload = BASELINE.json
+configs[1]: a 20-D correlated live set of 4000 points (reference helper recipe,
+tests/test_run.py:14-19), AffineLayer, MLFriends with a 30-round bootstrapped radius, proposals
+drawn with the reference's wrapping-ellipsoid recipe (mlfriends.pyx:1145-1154), Gaussian
+likelihood (docs/gauss.py:25-27).
+
+Printed (rank 0, one JSON line): ``value`` = device-resident throughput (inputs already in HBM),
+``e2e`` = the same metric through the C-ABI host call (pinned host buffers, H2D/D2H inside the
+timed region), ``roofline`` for the dominant kernel (first-neighbour scan), ``cpu_baseline`` =
+the unmodified reference (oracle/_ref) on this box's host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_LIVE = 4000
+NDIM = 20
+SIGMA = 0.01
+NBOOT = 30
+METRIC = "proposed-points/sec through MLFriends.inside + loglike, N_live=4000 d=20"
+
+
+# --------------------------------------------------------------------------------------
+# workload (pure NumPy; identical for both arms)
+# --------------------------------------------------------------------------------------
+def make_live(n=N_LIVE, d=NDIM, seed=1):
+    rng = np.random.RandomState(seed)
+    z = rng.normal(size=(n, d))
+    z /= ((z**2).sum(axis=1)**0.5).reshape((n, 1))
+    z *= rng.uniform(size=(n, 1))**(1. / d)
+    C = 0.5 * np.ones((d, d)) + 0.5 * np.eye(d)
+    L = np.linalg.cholesky(C)
+    return 0.5 + 0.05 * np.dot(z, L.T)
+
+
+def build_region(mod, u):
+    """mod = ultranest_b200.mlfriends (ours) or ultranest.mlfriends (reference)."""
+    layer = mod.AffineLayer()
+    layer.optimize(u, u)
+    region = mod.MLFriends(u, layer)
+    region.maxradiussq, region.enlarge = region.compute_enlargement(
+        nbootstraps=NBOOT, rng=np.random.RandomState(2))
+    region.create_ellipsoid()
+    return region
+
+
+def make_candidates(region, m, seed):
+    """The reference's sample_from_wrapping_ellipsoid draw (mlfriends.pyx:1145-1154), topped up
+    to exactly m rows inside the unit cube."""
+    rng = np.random.RandomState(seed)
+    d = region.u.shape[1]
+    out = np.empty((m, d))
+    filled = 0
+    while filled < m:
+        ns = int((m - filled) * 1.1) + 16
+        z = rng.normal(size=(ns, d))
+        z /= ((z**2).sum(axis=1)**0.5).reshape((ns, 1))
+        uu = z * region.enlarge**0.5 * rng.uniform(size=(ns, 1))**(1. / d)
+        w = region.ellipsoid_center + np.dot(uu, region.ellipsoid_axes_T)
+        w = w[np.logical_and(w > 0, w < 1).all(axis=1)]
+        take = min(len(w), m - filled)
+        out[filled:filled + take] = w[:take]
+        filled += take
+    return out
+
+
+def numpy_loglike(theta):
+    centers = 0.5
+    return -0.5 * (((theta - centers) / SIGMA)**2).sum(axis=1) - 0.5 * np.log(2 * np.pi * SIGMA**2) * NDIM
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# reference (CPU) arm
+# --------------------------------------------------------------------------------------
+_REF_STATE = {}
+
+
+def _ref_worker(chunk):
+    region = _REF_STATE["region"]
+    m = region.inside(chunk)
+    like = numpy_loglike(chunk[m])
+    return int(m.sum()), float(like.sum()) if len(like) else 0.0
+
+
+def reference_setup():
+    """Region + candidates with the reference implementation (oracle/_ref when built here,
+    else the oracle port)."""
+    import oracle
+    kind = "reference"
+    try:
+        oracle.reference()
+        import ultranest.mlfriends as refmod
+    except Exception:  # noqa: BLE001
+        refmod = None
+        kind = "port"
+    u = make_live()
+    if refmod is not None:
+        region = build_region(refmod, u)
+    else:
+        region = _PortRegion(u)
+    _REF_STATE["region"] = region
+    return region, kind
+
+
+class _PortRegion(object):
+    """Oracle-port stand-in with the same inside() contract (only when oracle/_ref is absent)."""
+
+    def __init__(self, u):
+        from oracle import cport
+        self.cport = cport
+        self.u = u
+        d = u.shape[1]
+        self.ctr = np.mean(u, axis=0)
+        cov = np.cov(u, rowvar=0) * (d + 2)
+        w, v = np.linalg.eigh(cov)
+        self.T = v * w**-0.5
+        self.unormed = np.dot(u - self.ctr, self.T)
+        self.maxradiussq, self.enlarge = cport.compute_enlargement(u, self.unormed, NBOOT, np.random.RandomState(2))
+        self.ellipsoid_center, ecov = cport.bounding_ellipsoid(u)
+        self.ellipsoid_invcov = np.linalg.inv(ecov)
+        l, vv = np.linalg.eigh(self.ellipsoid_invcov)
+        self.ellipsoid_axes_T = np.dot(vv, np.diag(1. / np.sqrt(l))).transpose()
+
+    def inside(self, pts):
+        return self.cport.region_inside(pts, self.unormed, lambda p: np.dot(p - self.ctr, self.T),
+                                        self.maxradiussq, self.ellipsoid_center,
+                                        self.ellipsoid_invcov, self.enlarge)
+
+
+def reference_throughput(steps, warmup, rows_per_core=65536, cores=None):
+    """Times `steps` bounded samples through region.inside + loglike on all host cores
+    (row-sharded over forked workers, which is what the reference's `mpiexec -np K` does)."""
+    import multiprocessing as mp
+    region, kind = reference_setup()
+    cores = cores or len(os.sched_getaffinity(0))
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    sample_rows = rows_per_core * cores
+    cand = make_candidates(region, sample_rows, 3)
+    chunks = np.array_split(cand, cores)
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker, chunks)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    accepted = sum(r[0] for r in res)
+    total = float(np.sum(times))
+    value = sample_rows * len(times) / total
+    return {"value": value, "unit": "points/s", "cores": cores, "kind": kind,
+            "sample": "%d wrapping-ellipsoid proposals per step (%d per core), %d steps, "
+                      "accept fraction %.3f" % (sample_rows, rows_per_core, len(times),
+                                                accepted / float(sample_rows)),
+            "ms_per_step": 1e3 * total / len(times), "rows": sample_rows}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    base = reference_throughput(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "20-D correlated Gaussian live set, N_live=4000, AffineLayer, "
+                               "MLFriends inside() + Gaussian loglike, wrapping-ellipsoid proposals",
+                   "rows_per_step": base["rows"], "n_live": N_LIVE, "ndim": NDIM},
+        "cpu_baseline": {"value": base["value"], "unit": "points/s", "cores": base["cores"],
+                         "kind": base["kind"], "sample": base["sample"]},
+        "e2e": {"value": base["value"], "unit": "points/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# ours
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes
+    import torch
+    from ultranest_b200 import _native
+    from ultranest_b200 import mlfriends as ours
+    from ultranest_b200.likelihoods import GaussianLogLike
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = _native.get_engine()
+    M = args.batch
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- region + proposals
+    u = make_live()
+    t0 = time.perf_counter()
+    region = build_region(ours, u)
+    rebuild_s = time.perf_counter() - t0
+    cand = make_candidates(region, M, 3 + rank)
+    loglike = GaussianLogLike(0.5, SIGMA)
+    kind, lparams = loglike.device_spec(NDIM)
+    region._bind()
+
+    stream = torch.cuda.current_stream()
+    sh = ctypes.c_void_p(stream.cuda_stream)
+    pts_dev = torch.from_numpy(cand).cuda()
+    mask_dev = torch.empty(M, dtype=torch.uint8, device="cuda")
+    like_dev = torch.empty(M, dtype=torch.float64, device="cuda")
+    lp = _native.as_f64(lparams)
+
+    def dev_step(first=False):
+        eng.call("unb_region_inside_loglike_dev", pts_dev.data_ptr(), M, mask_dev.data_ptr(),
+                 like_dev.data_ptr(), int(kind), lp.ctypes.data if first else None, sh)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- (1) device-resident value
+    dev_step(first=True)
+    for _ in range(W):
+        dev_step()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = eng.stat(_native.STAT_KERNEL_LAUNCHES)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        dev_step()
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.stat(_native.STAT_KERNEL_LAUNCHES) - launches0
+    accepted = int(mask_dev.sum().item())
+
+    # ---- (2) dominant kernel alone (first-neighbour scan over t-space proposals)
+    tcand = region.transformLayer.transform(cand)
+    t_dev = torch.from_numpy(tcand).cuda()
+    idx_dev = torch.empty(M, dtype=torch.int64, device="cuda")
+
+    def scan_step():
+        eng.call("unb_region_find_nearby_dev", t_dev.data_ptr(), M, idx_dev.data_ptr(), None, sh)
+
+    for _ in range(W):
+        scan_step()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(stream)
+    for _ in range(K):
+        scan_step()
+    k1.record(stream)
+    torch.cuda.synchronize()
+    scan_ms = k0.elapsed_time(k1) / K
+    idx_host = idx_dev.cpu().numpy()
+    # pair-dimensions the reference's early-exit loop evaluates for these proposals
+    scanned = np.where(idx_host >= 0, idx_host + 1, N_LIVE).astype(np.float64).sum()
+
+    # ---- (3) end to end through the C ABI with pinned host buffers
+    pin_pts = torch.empty((M, NDIM), dtype=torch.float64).pin_memory()
+    pin_pts.numpy()[...] = cand
+    pin_mask = torch.empty(M, dtype=torch.uint8).pin_memory()
+    pin_like = torch.empty(M, dtype=torch.float64).pin_memory()
+    np_pts, np_mask, np_like = pin_pts.numpy(), pin_mask.numpy().view(bool), pin_like.numpy()
+
+    def e2e_step():
+        eng.region_inside_loglike(np_pts, kind, lparams, mask_out=np_mask, like_out=np_like)
+
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    h2d0, d2h0 = eng.stat(_native.STAT_H2D_BYTES), eng.stat(_native.STAT_D2H_BYTES)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    h2d = (eng.stat(_native.STAT_H2D_BYTES) - h2d0) // K
+    d2h = (eng.stat(_native.STAT_D2H_BYTES) - d2h0) // K
+    clk = clocks.stop()
+    e2e_ok = bool((np_mask.view(np.uint8) == mask_dev.cpu().numpy()).all()) if world == 1 else True
+
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the scan kernel (HBM roofline as BASELINE.json prescribes; see DESIGN.md
+    # for why the fp64 pipe, not HBM, is the binding ceiling of this kernel)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = M * (8.0 * NDIM + 8.0) + N_LIVE * NDIM * 8.0
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "k_scan_reg<20,2,FIND> (first-neighbour scan)",
+        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+        "traffic": None, "ms_per_launch": scan_ms,
+        "fp64": {"pair_dims_per_s": scanned * NDIM / (scan_ms * 1e-3),
+                 "algorithmic_flop_per_s": 3.0 * scanned * NDIM / (scan_ms * 1e-3),
+                 "nominal_fp64_peak_flop_per_s": 40e12,
+                 "note": "reference-equivalent work (3 flop per pair-dimension the Cython loop "
+                         "would evaluate) / time; nominal B200 fp64 peak, not measured"},
+    }
+    line = {
+        "metric": METRIC, "value": world * M * K / (dev_ms * 1e-3), "unit": "points/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 20-D correlated Gaussian live set, N_live=4000, "
+                               "AffineLayer, MLFriends.inside() + Gaussian loglike, "
+                               "wrapping-ellipsoid proposals (accepting regime)",
+                   "rows_per_step_per_gpu": M, "n_live": N_LIVE, "ndim": NDIM,
+                   "l2_policy": "inputs larger than L2 (%.0f MB of proposals per step)" % (M * NDIM * 8 / 1e6),
+                   "parallelism": "proposal rows sharded over %d GPU(s), no data-path collective" % world,
+                   "accept_fraction": accepted / float(M), "region_rebuild_s": rebuild_s,
+                   "maxradiussq": region.maxradiussq, "enlarge": region.enlarge},
+        "e2e": {"value": world * M * K / (e2e_ms * 1e-3), "unit": "points/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms / K, "matches_device_path": e2e_ok,
+                "call": "unb_region_inside_loglike (pinned host buffers, chunked double-buffered)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "clocks": clk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            base = reference_throughput(steps=3, warmup=1, rows_per_core=32768)
+            line["cpu_baseline"] = {"value": base["value"], "unit": "points/s",
+                                    "cores": base["cores"], "kind": base["kind"],
+                                    "sample": base["sample"]}
+        except Exception as exc:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "port",
+                                    "sample": "failed: %s" % exc}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="proposals per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,204 @@
+/*
+ * ultranest_b200.h -- C ABI of the B200-native MLFriends region engine.
+ *
+ * This is the drop-in boundary for ONE hot path of JohannesBuchner/UltraNest: the MLFriends
+ * region subsystem of ultranest/mlfriends.pyx plus the vectorised-likelihood batch call.
+ * Every entry point names the reference interface it replaces (file:line relative to the
+ * reference checkout).  Conventions, all taken from the reference's own foreign-function
+ * precedent (languages/c/mylib.c:24-41, languages/c/runc.py:8-28):
+ *
+ *   - plain pointers and sizes only; arrays are C-contiguous, row-major, float64 unless
+ *     stated; indices are int64 (mlfriends.pyx:25-26); masks are 1 byte per row (NumPy bool);
+ *   - the CALLER owns every host buffer, outputs are caller-allocated (mlfriends.pyx:147:
+ *     `nnearby` is an out-parameter); the library owns device memory behind `unb_ctx`;
+ *     no host pointer is retained after a call returns;
+ *   - every function returns UNB_OK (0) or a negative UNB_ERR_* code; the message is at
+ *     unb_last_error(ctx).  The Python shim maps codes to the reference's exception types;
+ *   - one host thread per ctx, results are valid on return (synchronous semantics), except
+ *     the `_dev` variants, which take DEVICE pointers (e.g. torch.Tensor.data_ptr()) plus a
+ *     cudaStream_t (as void*; NULL = the ctx's own stream) and only enqueue work.
+ *
+ * There is no CPU fallback anywhere behind this ABI: a missing/unsupported GPU is an error.
+ */
+#ifndef ULTRANEST_B200_H
+#define ULTRANEST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNB_ABI_VERSION 1
+
+#define UNB_OK 0
+#define UNB_ERR_CUDA (-1)        /* CUDA runtime/driver failure (incl. no device)        */
+#define UNB_ERR_ARG (-2)         /* bad argument (shape mismatch, NULL, d too large ...) */
+#define UNB_ERR_STATE (-3)       /* region state incomplete for the requested call       */
+#define UNB_ERR_NOMEM (-4)       /* host or device allocation failed                     */
+#define UNB_ERR_NUMERIC (-5)     /* non-positive distances etc. (-> LinAlgError)         */
+
+/* unb_ctx_set_option keys */
+#define UNB_OPT_EXACT_ONLY 1     /* 1: bypass the filtered scans, run the plain exact-order
+                                    kernels (slow; for validation)                        */
+#define UNB_OPT_CHUNK_ROWS 2     /* rows per H2D/compute/D2H pipeline chunk (host API)    */
+
+/* unb_ctx_get_stat keys */
+#define UNB_STAT_KERNEL_LAUNCHES 1   /* kernels launched by this ctx since creation       */
+#define UNB_STAT_RECHECKS 2          /* filtered-scan pairs that went to the exact path
+                                        in the last scan call (diagnostic)                */
+#define UNB_STAT_H2D_BYTES 3
+#define UNB_STAT_D2H_BYTES 4
+
+/* transform-layer kinds for unb_region_set_layer */
+#define UNB_LAYER_IDENTITY 0
+#define UNB_LAYER_SCALING 1      /* ScalingLayer.transform, mlfriends.pyx:605-611          */
+#define UNB_LAYER_AFFINE 2       /* AffineLayer.transform,  mlfriends.pyx:737-743          */
+
+/* likelihood kinds for the fused inside+loglike call */
+#define UNB_LOGLIKE_NONE 0
+#define UNB_LOGLIKE_GAUSS 1
+#define UNB_LOGLIKE_EGGBOX 2
+#define UNB_LOGLIKE_ROSENBROCK 3
+
+typedef struct unb_ctx unb_ctx;
+
+/* ------------------------------------------------------------------ context */
+int unb_abi_version(void);
+int unb_ctx_create(int device, unb_ctx **out);
+int unb_ctx_destroy(unb_ctx *ctx);
+const char *unb_last_error(const unb_ctx *ctx);
+int unb_ctx_set_option(unb_ctx *ctx, int option, int64_t value);
+int unb_ctx_get_stat(unb_ctx *ctx, int stat, int64_t *value);
+int unb_ctx_synchronize(unb_ctx *ctx);
+
+/* --------------------------------------------- stateless scans (host buffers) */
+
+/* replaces find_nearby(apts, bpts, radiussq, nnearby), mlfriends.pyx:143-183:
+ * nnearby[j] = FIRST i with ||apts[i]-bpts[j]||^2 <= radiussq (fp64, k-sequential,
+ * non-fused), else -1.  Bit-exact. */
+int unb_find_nearby(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
+                    size_t nb, size_t ndim, double radiussq, int64_t *nnearby);
+
+/* replaces count_nearby (cdef), mlfriends.pyx:31-68: number of i within radiussq. */
+int unb_count_nearby(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
+                     size_t nb, size_t ndim, double radiussq, int64_t *nnearby);
+
+/* replaces _subtract_nearby(apts, bpts, radiussq), mlfriends.pyx:73-113. */
+int unb_subtract_nearby(unb_ctx *ctx, const double *apts, size_t n, size_t ndim,
+                        double radiussq, double *bpts_out);
+
+/* replaces compute_maxradiussq(apts, bpts) (cdef float), mlfriends.pyx:188-224:
+ * max_j min_i ||a_i-b_j||^2, returned rounded to float32 like the C `float` return. */
+int unb_compute_maxradiussq(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
+                            size_t nb, size_t ndim, double *maxd_out);
+
+/* replaces compute_mean_pair_distance(pts, clusterids), mlfriends.pyx:229-270.
+ * (Deterministic but tree-ordered sum: agrees with the sequential reference to ~1e-13
+ * relative, not bit-exact; documented in DESIGN.md.) */
+int unb_mean_pair_distance(unb_ctx *ctx, const double *pts, const int64_t *clusterids,
+                           size_t n, size_t ndim, double *out);
+
+/* replaces _inside_ellipsoid(points, center, invcov, square_radius), mlfriends.pyx:882-912
+ * (einsum 'ij,jk,ik->i' order: acc += (d_j*A_jk)*d_k, j outer, k inner; `<=`). Bit-exact. */
+int unb_inside_ellipsoid(unb_ctx *ctx, const double *points, size_t m, size_t ndim,
+                         const double *center, const double *invcov, double square_radius,
+                         uint8_t *mask);
+
+/* replace ScalingLayer/AffineLayer.transform / .untransform, mlfriends.pyx:605-620, 737-752.
+ * Scaling is bit-exact; affine uses the DEFINED order (k-sequential FMA) because the
+ * reference's np.dot is BLAS-kernel specific (see DESIGN.md "Affine transform"). */
+int unb_transform_scaling(unb_ctx *ctx, const double *w, size_t m, size_t ndim,
+                          const double *mean, const double *std, double *out);
+int unb_untransform_scaling(unb_ctx *ctx, const double *ww, size_t m, size_t ndim,
+                            const double *mean, const double *std, double *out);
+int unb_transform_affine(unb_ctx *ctx, const double *w, size_t m, size_t ndim,
+                         const double *ctr, const double *T, double *out);
+int unb_untransform_affine(unb_ctx *ctx, const double *ww, size_t m, size_t ndim,
+                           const double *ctr, const double *invT, double *out);
+
+/* ------------------------------------------------- stateful region (device mirror) */
+
+/* Mirror of MLFriends.unormed (the t-space live block, mlfriends.pyx:982).  The library
+ * keeps a host snapshot; calling this again with a mutated array (integrator.py:2753-2754
+ * patches rows in place) re-uploads only the rows that changed.  *rows_changed may be NULL. */
+int unb_region_sync_live(unb_ctx *ctx, const double *unormed, size_t n, size_t ndim,
+                         int64_t *rows_changed);
+
+/* transformLayer parameters used for candidates: kind SCALING: shift=mean[d], mat=std[d];
+ * AFFINE: shift=ctr[d], mat=T[d*d]; IDENTITY: both NULL. */
+int unb_region_set_layer(unb_ctx *ctx, int kind, const double *shift, const double *mat,
+                         size_t ndim);
+
+/* MLFriends.ellipsoid_center / ellipsoid_invcov / enlarge (mlfriends.pyx:1226-1227, 1254). */
+int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, const double *invcov,
+                             double enlarge, size_t ndim);
+
+/* MLFriends.maxradiussq */
+int unb_region_set_radius(unb_ctx *ctx, double maxradiussq);
+
+/* replaces MLFriends.inside(pts), mlfriends.pyx:1186-1211 (ellipsoid -> transform ->
+ * find_nearby >= 0) in one device pipeline.  idx_out (optional, may be NULL) receives the
+ * first-neighbour index or -1. */
+int unb_region_inside(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
+                      int64_t *idx_out);
+int unb_region_inside_dev(unb_ctx *ctx, const double *pts_dev, size_t m, uint8_t *mask_dev,
+                          void *stream);
+
+/* find_nearby / count_nearby of t-space candidates against the mirrored live block
+ * (mlfriends.pyx:1110, 1125, 1157, 1088). */
+int unb_region_find_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby);
+int unb_region_count_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby);
+/* device-pointer variant of the scan alone (nnearby_dev or mask_dev may be NULL) */
+int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, size_t m,
+                               int64_t *nnearby_dev, uint8_t *mask_dev, void *stream);
+
+/* Bootstrapped radius + ellipsoid enlargement, the device half of
+ * MLFriends.compute_enlargement (mlfriends.pyx:1044-1066) for `nrounds` rounds at once:
+ *   selected : nrounds x n bytes, the rounds' selection masks (host RNG, reference order);
+ *   unormed  : n x d, t-space live block (NULL with maxd_out NULL: skip the radius scan);
+ *   u        : n x d, u-space live block (NULL: skip the enlargement);
+ *   ctrs     : nrounds x d, invcovs: nrounds x d x d, per-round bounding_ellipsoid centre and
+ *              inv(cov) from the host (LAPACK stays on the host, as in the reference);
+ *   maxd_out : nrounds, compute_maxradiussq(unormed[sel], unormed[~sel]) rounded to float32;
+ *   f_out    : nrounds, einsum('ij,jk,ik->i', u[~sel]-ctr, a, u[~sel]-ctr).max()
+ *              (skipped when u/ctrs/invcovs/f_out is NULL).
+ * round_lo/round_hi select the slice of rounds this process computes (multi-GPU sharding,
+ * integrator.py:388-404); other entries of the outputs are left untouched. */
+int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const double *u, size_t n,
+                         size_t ndim, const uint8_t *selected, size_t nrounds,
+                         size_t round_lo, size_t round_hi, const double *ctrs,
+                         const double *invcovs, double *maxd_out, double *f_out);
+
+/* ---------------------------------------------- vectorised likelihood batch call */
+
+/* Same (params, d, n, like) shape as languages/c/mylib.c:33 my_c_likelihood_vectorized. */
+/* docs/gauss.py:25-27; norm_const = 0.5*log(2*pi*sigma^2)*d evaluated by the host. Bit-exact
+ * w.r.t. NumPy (pairwise-sum order reproduced). */
+int unb_loglike_gauss(unb_ctx *ctx, const double *params, size_t d, size_t n, double *like,
+                      const double *centers, double sigma, double norm_const);
+/* examples/testrosenbrock.py:10-13. Bit-exact w.r.t. NumPy. */
+int unb_loglike_rosenbrock(unb_ctx *ctx, const double *params, size_t d, size_t n,
+                           double *like);
+/* examples/testeggbox.py:9-11 (cos/pow: few-ulp parity, not bit-exact). */
+int unb_loglike_eggbox(unb_ctx *ctx, const double *params, size_t d, size_t n, double *like);
+
+int unb_loglike_gauss_dev(unb_ctx *ctx, const double *params_dev, size_t d, size_t n,
+                          double *like_dev, const uint8_t *mask_dev, const double *centers,
+                          double sigma, double norm_const, void *stream);
+
+/* Fused proposal evaluation (integrator.py:1776-1804 without the host
+ * compaction): mask = region.inside(pts); like[j] = loglike(pts[j]) where mask[j], else -inf.
+ * One H2D of pts, D2H of mask+like.  lparams: GAUSS -> centers[d], sigma, norm_const packed as
+ * d+2 doubles; others NULL. */
+int unb_region_inside_loglike(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
+                              double *like, int loglike_kind, const double *lparams);
+int unb_region_inside_loglike_dev(unb_ctx *ctx, const double *pts_dev, size_t m,
+                                  uint8_t *mask_dev, double *like_dev, int loglike_kind,
+                                  const double *lparams, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULTRANEST_B200_H */

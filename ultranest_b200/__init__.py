@@ -1,0 +1,44 @@
+"""B200-native MLFriends region engine for UltraNest.
+
+One hot path of JohannesBuchner/UltraNest -- the MLFriends region subsystem of
+``ultranest/mlfriends.pyx`` plus the vectorised-likelihood batch call -- rebuilt as
+hand-written sm_100a CUDA kernels behind a C ABI (``include/ultranest_b200.h``), with this
+package as the host-side mirror of the reference's Python interface.
+
+Use it from an unmodified UltraNest either per run::
+
+    from ultranest_b200.mlfriends import MLFriends, LocalAffineLayer
+    sampler.transform_layer_class = LocalAffineLayer
+    sampler.run(region_class=MLFriends)
+
+or process-wide, before ``ultranest.integrator`` is imported::
+
+    import ultranest_b200; ultranest_b200.install()
+"""
+import sys
+
+__version__ = "0.1.0"
+
+
+def install(force=False):
+    """Make ``import ultranest.mlfriends`` resolve to :mod:`ultranest_b200.mlfriends`.
+
+    ``ultranest/integrator.py`` binds ``MLFriends``, ``AffineLayer``, ``WrappingEllipsoid``,
+    ``find_nearby`` ... by name at import time (integrator.py:28-30), so this must run before
+    the integrator is imported (``force=True`` also re-binds an already imported integrator).
+    """
+    from . import mlfriends as ours
+    already = sys.modules.get("ultranest.integrator")
+    sys.modules["ultranest.mlfriends"] = ours
+    pkg = sys.modules.get("ultranest")
+    if pkg is not None:
+        pkg.mlfriends = ours
+    if already is not None:
+        if not force:
+            raise RuntimeError("ultranest.integrator is already imported; call "
+                               "ultranest_b200.install() first or pass force=True")
+        for name in ("AffineLayer", "LocalAffineLayer", "MLFriends", "RobustEllipsoidRegion",
+                     "ScalingLayer", "WrappingEllipsoid", "find_nearby"):
+            if hasattr(already, name):
+                setattr(already, name, getattr(ours, name))
+    return ours

@@ -1,0 +1,423 @@
+"""ctypes binding of ``libultranest_b200.so`` (the C ABI in ``include/ultranest_b200.h``).
+
+There is deliberately no CPU fallback: if the CUDA library cannot be loaded, or no sm_100
+device is visible, importing the engine raises.  PyTorch is not needed here; it is only the
+container for device-resident arrays in :mod:`ultranest_b200.device`.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+UNB_OK = 0
+UNB_ERR_CUDA = -1
+UNB_ERR_ARG = -2
+UNB_ERR_STATE = -3
+UNB_ERR_NOMEM = -4
+UNB_ERR_NUMERIC = -5
+
+OPT_EXACT_ONLY = 1
+OPT_CHUNK_ROWS = 2
+STAT_KERNEL_LAUNCHES = 1
+STAT_RECHECKS = 2
+STAT_H2D_BYTES = 3
+STAT_D2H_BYTES = 4
+
+LAYER_IDENTITY = 0
+LAYER_SCALING = 1
+LAYER_AFFINE = 2
+
+LOGLIKE_NONE = 0
+LOGLIKE_GAUSS = 1
+LOGLIKE_EGGBOX = 2
+LOGLIKE_ROSENBROCK = 3
+
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_c_ip = ctypes.POINTER(ctypes.c_int64)
+_c_bp = ctypes.POINTER(ctypes.c_uint8)
+_c_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_dbl = ctypes.c_double
+_int = ctypes.c_int
+_i64 = ctypes.c_int64
+
+# name -> argtypes (after the leading ctx pointer); every symbol of include/ultranest_b200.h
+SIGNATURES = {
+    "unb_ctx_destroy": [],
+    "unb_ctx_set_option": [_int, _i64],
+    "unb_ctx_get_stat": [_int, _c_ip],
+    "unb_ctx_synchronize": [],
+    "unb_find_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
+    "unb_count_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
+    "unb_subtract_nearby": [_c_vp, _sz, _sz, _dbl, _c_vp],
+    "unb_compute_maxradiussq": [_c_vp, _sz, _c_vp, _sz, _sz, _c_dp],
+    "unb_mean_pair_distance": [_c_vp, _c_vp, _sz, _sz, _c_dp],
+    "unb_inside_ellipsoid": [_c_vp, _sz, _sz, _c_vp, _c_vp, _dbl, _c_vp],
+    "unb_transform_scaling": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp],
+    "unb_untransform_scaling": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp],
+    "unb_transform_affine": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp],
+    "unb_untransform_affine": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp],
+    "unb_region_sync_live": [_c_vp, _sz, _sz, _c_ip],
+    "unb_region_set_layer": [_int, _c_vp, _c_vp, _sz],
+    "unb_region_set_ellipsoid": [_c_vp, _c_vp, _dbl, _sz],
+    "unb_region_set_radius": [_dbl],
+    "unb_region_inside": [_c_vp, _sz, _c_vp, _c_vp],
+    "unb_region_inside_dev": [_c_vp, _sz, _c_vp, _c_vp],
+    "unb_region_find_nearby": [_c_vp, _sz, _c_vp],
+    "unb_region_count_nearby": [_c_vp, _sz, _c_vp],
+    "unb_region_find_nearby_dev": [_c_vp, _sz, _c_vp, _c_vp, _c_vp],
+    "unb_region_bootstrap": [_c_vp, _c_vp, _sz, _sz, _c_vp, _sz, _sz, _sz, _c_vp, _c_vp,
+                             _c_vp, _c_vp],
+    "unb_loglike_gauss": [_c_vp, _sz, _sz, _c_vp, _c_vp, _dbl, _dbl],
+    "unb_loglike_rosenbrock": [_c_vp, _sz, _sz, _c_vp],
+    "unb_loglike_eggbox": [_c_vp, _sz, _sz, _c_vp],
+    "unb_loglike_gauss_dev": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp, _dbl, _dbl, _c_vp],
+    "unb_region_inside_loglike": [_c_vp, _sz, _c_vp, _c_vp, _int, _c_vp],
+    "unb_region_inside_loglike_dev": [_c_vp, _sz, _c_vp, _c_vp, _int, _c_vp, _c_vp],
+}
+# symbols without the leading ctx argument
+FREE_SIGNATURES = {
+    "unb_abi_version": ([], _int),
+    "unb_ctx_create": ([_int, ctypes.POINTER(_c_vp)], _int),
+    "unb_last_error": ([_c_vp], ctypes.c_char_p),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class NativeLibraryError(ImportError):
+    """The CUDA library is missing or cannot be loaded (there is no CPU fallback)."""
+
+
+def library_path():
+    return _build.LIBPATH
+
+
+def load_library():
+    """dlopen the in-tree library (building it with nvcc when missing) and set signatures."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIBPATH
+        if not os.path.exists(path):
+            try:
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise NativeLibraryError(
+                    "libultranest_b200.so is not built and nvcc could not build it (%s); "
+                    "run `python -m ultranest_b200.build`" % exc)
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as exc:
+            raise NativeLibraryError("cannot load %s: %s" % (path, exc))
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = [_c_vp] + list(args)
+            fn.restype = _int
+        for name, (args, res) in FREE_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = list(args)
+            fn.restype = res
+        _lib = lib
+        return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def as_f64(a, ndim=None):
+    """C-contiguous float64 view/copy (callers pass boolean-masked copies and slices)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if ndim is not None and a.ndim != ndim:
+        raise ValueError("expected a %d-d array, got shape %s" % (ndim, a.shape))
+    return a
+
+
+class Engine(object):
+    """One ``unb_ctx`` (one CUDA device, one host thread)."""
+
+    def __init__(self, device=None):
+        self.lib = load_library()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", os.environ.get("UNB_DEVICE", "0")))
+        handle = _c_vp()
+        rc = self.lib.unb_ctx_create(int(device), ctypes.byref(handle))
+        if rc != UNB_OK or not handle.value:
+            raise RuntimeError(
+                "ultranest_b200: cannot create a CUDA context on device %d (rc=%d). "
+                "This package needs an sm_100 (B200) GPU; there is no CPU fallback." % (device, rc))
+        self.device = int(device)
+        self.ctx = handle
+        self._bound = None      # id of the region object whose state the ctx mirrors
+
+    # -- plumbing --------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx.value:
+            self.lib.unb_ctx_destroy(self.ctx)
+            self.ctx = _c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def error(self):
+        msg = self.lib.unb_last_error(self.ctx)
+        return msg.decode("utf-8", "replace") if msg else ""
+
+    def check(self, rc):
+        if rc == UNB_OK:
+            return
+        msg = "ultranest_b200: %s" % self.error()
+        if rc == UNB_ERR_NUMERIC:
+            raise np.linalg.LinAlgError(msg)
+        if rc == UNB_ERR_ARG:
+            raise ValueError(msg)
+        if rc == UNB_ERR_NOMEM:
+            raise MemoryError(msg)
+        raise RuntimeError(msg + " (rc=%d)" % rc)
+
+    def call(self, name, *args):
+        self.check(getattr(self.lib, name)(self.ctx, *args))
+
+    def set_option(self, option, value):
+        self.call("unb_ctx_set_option", option, int(value))
+
+    def stat(self, key):
+        v = _i64(0)
+        self.call("unb_ctx_get_stat", key, ctypes.byref(v))
+        return int(v.value)
+
+    def synchronize(self):
+        self.call("unb_ctx_synchronize")
+
+    # -- stateless scans ---------------------------------------------------------------
+    def find_nearby(self, apts, bpts, radiussq, out=None):
+        a = as_f64(apts, 2)
+        b = as_f64(bpts, 2)
+        if a.shape[1] != b.shape[1]:
+            raise ValueError("dimensionality mismatch: %s vs %s" % (a.shape, b.shape))
+        res = out if _direct_out(out, len(b), np.int64) else np.empty(len(b), dtype=np.int64)
+        self.call("unb_find_nearby", _ptr(a), len(a), _ptr(b), len(b), b.shape[1],
+                  float(radiussq), _ptr(res))
+        if out is not None and res is not out:
+            out[:len(b)] = res
+            return out
+        return res
+
+    def count_nearby(self, apts, bpts, radiussq, out=None):
+        a = as_f64(apts, 2)
+        b = as_f64(bpts, 2)
+        if a.shape[1] != b.shape[1]:
+            raise ValueError("dimensionality mismatch: %s vs %s" % (a.shape, b.shape))
+        res = out if _direct_out(out, len(b), np.int64) else np.empty(len(b), dtype=np.int64)
+        self.call("unb_count_nearby", _ptr(a), len(a), _ptr(b), len(b), b.shape[1],
+                  float(radiussq), _ptr(res))
+        if out is not None and res is not out:
+            out[:len(b)] = res
+            return out
+        return res
+
+    def subtract_nearby(self, apts, radiussq, out=None):
+        a = as_f64(apts, 2)
+        res = out if _direct_out(out, a.shape, np.float64) else np.empty_like(a)
+        self.call("unb_subtract_nearby", _ptr(a), a.shape[0], a.shape[1], float(radiussq), _ptr(res))
+        if out is not None and res is not out:
+            out[...] = res
+            return out
+        return res
+
+    def compute_maxradiussq(self, apts, bpts):
+        a = as_f64(apts, 2)
+        b = as_f64(bpts, 2)
+        if a.shape[1] != b.shape[1]:
+            raise ValueError("dimensionality mismatch: %s vs %s" % (a.shape, b.shape))
+        out = _dbl(0.0)
+        self.call("unb_compute_maxradiussq", _ptr(a), len(a), _ptr(b), len(b), a.shape[1],
+                  ctypes.byref(out))
+        return float(out.value)
+
+    def mean_pair_distance(self, pts, clusterids):
+        p = as_f64(pts, 2)
+        c = np.ascontiguousarray(clusterids, dtype=np.int64)
+        if len(c) < len(p):
+            raise ValueError("clusterids shorter than pts")
+        out = _dbl(0.0)
+        self.call("unb_mean_pair_distance", _ptr(p), _ptr(c), len(p), p.shape[1], ctypes.byref(out))
+        return float(out.value)
+
+    def inside_ellipsoid(self, points, center, invcov, square_radius):
+        p = as_f64(points, 2)
+        c = as_f64(center, 1)
+        A = as_f64(invcov, 2)
+        d = p.shape[1]
+        if c.shape != (d,) or A.shape != (d, d):
+            raise ValueError("ellipsoid shape mismatch: points %s center %s invcov %s"
+                             % (p.shape, c.shape, A.shape))
+        mask = np.empty(len(p), dtype=bool)
+        self.call("unb_inside_ellipsoid", _ptr(p), len(p), d, _ptr(c), _ptr(A),
+                  float(square_radius), _ptr(mask))
+        return mask
+
+    def transform(self, kind, inverse, pts, shift, mat):
+        p = as_f64(pts)
+        shape = p.shape
+        p2 = p.reshape((-1, shape[-1]))
+        d = p2.shape[1]
+        s = as_f64(np.ravel(shift))
+        m = as_f64(mat)
+        if kind == LAYER_AFFINE:
+            if s.shape != (d,) or m.shape != (d, d):
+                raise ValueError("affine layer shape mismatch")
+            name = "unb_untransform_affine" if inverse else "unb_transform_affine"
+        else:
+            m = as_f64(np.ravel(m))
+            if s.shape != (d,) or m.shape != (d,):
+                raise ValueError("scaling layer shape mismatch")
+            name = "unb_untransform_scaling" if inverse else "unb_transform_scaling"
+        out = np.empty_like(p2)
+        self.call(name, _ptr(p2), len(p2), d, _ptr(s), _ptr(m), _ptr(out))
+        return out.reshape(shape)
+
+    # -- stateful region -----------------------------------------------------------------
+    def region_sync_live(self, unormed):
+        t = as_f64(unormed, 2)
+        changed = _i64(0)
+        self.call("unb_region_sync_live", _ptr(t), t.shape[0], t.shape[1], ctypes.byref(changed))
+        return int(changed.value)
+
+    def region_set_layer(self, kind, shift=None, mat=None, ndim=0):
+        if kind == LAYER_IDENTITY:
+            self.call("unb_region_set_layer", kind, None, None, int(ndim))
+            return
+        s = as_f64(np.ravel(shift))
+        m = as_f64(mat) if kind == LAYER_AFFINE else as_f64(np.ravel(mat))
+        self.call("unb_region_set_layer", kind, _ptr(s), _ptr(m), len(s))
+
+    def region_set_ellipsoid(self, center, invcov, enlarge):
+        c = as_f64(center, 1)
+        A = as_f64(invcov, 2)
+        if A.shape != (len(c), len(c)):
+            raise ValueError("ellipsoid shape mismatch")
+        self.call("unb_region_set_ellipsoid", _ptr(c), _ptr(A), float(enlarge), len(c))
+
+    def region_set_radius(self, maxradiussq):
+        self.call("unb_region_set_radius", float(maxradiussq))
+
+    def region_inside(self, pts, want_index=False):
+        p = as_f64(pts, 2)
+        mask = np.empty(len(p), dtype=bool)
+        idx = np.empty(len(p), dtype=np.int64) if want_index else None
+        self.call("unb_region_inside", _ptr(p), len(p), _ptr(mask), _ptr(idx))
+        return (mask, idx) if want_index else mask
+
+    def region_find_nearby(self, tpts):
+        p = as_f64(tpts, 2)
+        out = np.empty(len(p), dtype=np.int64)
+        self.call("unb_region_find_nearby", _ptr(p), len(p), _ptr(out))
+        return out
+
+    def region_count_nearby(self, tpts):
+        p = as_f64(tpts, 2)
+        out = np.empty(len(p), dtype=np.int64)
+        self.call("unb_region_count_nearby", _ptr(p), len(p), _ptr(out))
+        return out
+
+    def region_bootstrap(self, unormed, selected, u=None, ctrs=None, invcovs=None,
+                         round_lo=0, round_hi=None):
+        """Per-round ``(maxd, f)`` of the bootstrap (either half may be skipped:
+        ``unormed=None`` skips the radius scan, ``u=None`` the enlargement)."""
+        want_d = unormed is not None
+        want_f = u is not None and ctrs is not None and invcovs is not None
+        if not (want_d or want_f):
+            raise ValueError("nothing to compute")
+        t = as_f64(unormed, 2) if want_d else None
+        if want_f:
+            u = as_f64(u, 2)
+        n, d = (t if want_d else u).shape
+        sel = np.ascontiguousarray(selected, dtype=np.uint8)
+        if sel.ndim != 2 or sel.shape[1] != n:
+            raise ValueError("selected must be (nrounds, n)")
+        nrounds = sel.shape[0]
+        if round_hi is None:
+            round_hi = nrounds
+        maxd = np.zeros(nrounds) if want_d else None
+        f = np.zeros(nrounds) if want_f else None
+        if want_f:
+            ctrs = as_f64(ctrs, 2)
+            invcovs = as_f64(invcovs, 3)
+            if u.shape != (n, d) or ctrs.shape != (nrounds, d) or invcovs.shape != (nrounds, d, d):
+                raise ValueError("bootstrap ellipsoid shapes mismatch")
+        self.call("unb_region_bootstrap", _ptr(t), _ptr(u) if want_f else None, n, d,
+                  _ptr(sel), nrounds, int(round_lo), int(round_hi),
+                  _ptr(ctrs) if want_f else None, _ptr(invcovs) if want_f else None,
+                  _ptr(maxd), _ptr(f))
+        return maxd, f
+
+    # -- likelihoods -----------------------------------------------------------------------
+    def loglike_gauss(self, theta, centers, sigma, norm_const):
+        p = as_f64(theta, 2)
+        c = as_f64(np.broadcast_to(centers, (p.shape[1],)))
+        out = np.empty(len(p))
+        self.call("unb_loglike_gauss", _ptr(p), p.shape[1], len(p), _ptr(out), _ptr(c),
+                  float(sigma), float(norm_const))
+        return out
+
+    def loglike_rosenbrock(self, theta):
+        p = as_f64(theta, 2)
+        out = np.empty(len(p))
+        self.call("unb_loglike_rosenbrock", _ptr(p), p.shape[1], len(p), _ptr(out))
+        return out
+
+    def loglike_eggbox(self, z):
+        p = as_f64(z, 2)
+        out = np.empty(len(p))
+        self.call("unb_loglike_eggbox", _ptr(p), p.shape[1], len(p), _ptr(out))
+        return out
+
+    def region_inside_loglike(self, pts, kind, lparams=None, mask_out=None, like_out=None):
+        p = as_f64(pts, 2)
+        mask = mask_out if mask_out is not None else np.empty(len(p), dtype=bool)
+        like = like_out if like_out is not None else np.empty(len(p))
+        lp = as_f64(lparams) if lparams is not None else None
+        self.call("unb_region_inside_loglike", _ptr(p), len(p), _ptr(mask), _ptr(like),
+                  int(kind), _ptr(lp))
+        return mask, like
+
+
+def _direct_out(out, shape, dtype):
+    """Can the library write straight into the caller's out-array?"""
+    if out is None or not isinstance(out, np.ndarray):
+        return False
+    if out.dtype != dtype or not out.flags.c_contiguous or not out.flags.writeable:
+        return False
+    want = shape if isinstance(shape, tuple) else (shape,)
+    return out.shape == want
+
+
+_engine = None
+_engine_lock = threading.Lock()
+
+
+def get_engine():
+    """Process-wide engine (device = $LOCAL_RANK, else $UNB_DEVICE, else 0)."""
+    global _engine
+    with _engine_lock:
+        if _engine is None:
+            _engine = Engine()
+        return _engine
+
+
+def reset_engine():
+    global _engine
+    with _engine_lock:
+        if _engine is not None:
+            _engine.close()
+        _engine = None

@@ -1,0 +1,54 @@
+"""Builds ``libultranest_b200.so`` (sm_100a) in-tree with nvcc.
+
+The library is compiled with ``-fmad=false`` so that no multiply-add is contracted unless the
+source says ``fma()`` -- the bit-exactness contract of the kernels depends on it.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "_lib")
+LIBPATH = os.path.join(LIBDIR, "libultranest_b200.so")
+SOURCES = ["unb_api.cu", "unb_region.cu", "unb_scan.cu"]
+HEADERS = ["unb_internal.cuh", os.path.join("..", "..", "include", "ultranest_b200.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libultranest_b200.so")
+
+
+def is_stale():
+    if not os.path.exists(LIBPATH):
+        return True
+    t = os.path.getmtime(LIBPATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False, extra_flags=()):
+    """Compile the CUDA library if missing or older than its sources."""
+    if not force and not is_stale():
+        return LIBPATH
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIBPATH] + SOURCES
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("nvcc failed building libultranest_b200.so")
+    if verbose and res.stdout:
+        print(res.stdout)
+    return LIBPATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

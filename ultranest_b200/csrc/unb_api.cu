@@ -1,0 +1,1078 @@
+// unb_api.cu -- extern "C" entry points declared in include/ultranest_b200.h: context
+// management, host<->device staging (pinned, double-buffered lanes) and the orchestration
+// of the kernels in unb_scan.cu / unb_region.cu.  No compute happens on the host here.
+#include "unb_internal.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <new>
+
+// ---------------------------------------------------------------------------------------
+// infrastructure
+// ---------------------------------------------------------------------------------------
+int unb_fail(unb_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int unb_reserve(unb_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return UNB_OK;
+    if (b.p) {
+        // buffers may still be in use by enqueued work of either lane
+        UNB_CUDA(ctx, cudaDeviceSynchronize());
+        UNB_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t cap = bytes + bytes / 4;
+    cap = (cap + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return unb_fail(ctx, UNB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+    }
+    b.cap = cap;
+    return UNB_OK;
+}
+
+int unb_reserve_pinned(unb_ctx *ctx, PinBuf &b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return UNB_OK;
+    if (b.p) {
+        UNB_CUDA(ctx, cudaDeviceSynchronize());
+        UNB_CUDA(ctx, cudaFreeHost(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t cap = bytes + bytes / 4;
+    cudaError_t e = cudaMallocHost(&b.p, cap);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return unb_fail(ctx, UNB_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", cap, cudaGetErrorString(e));
+    }
+    b.cap = cap;
+    return UNB_OK;
+}
+
+namespace {
+
+void free_dev(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+void free_pin(PinBuf &b)
+{
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+void free_live(LiveTiles &L)
+{
+    free_dev(L.tiles); free_dev(L.rows); free_dev(L.norms); free_dev(L.namax);
+    L.valid = false;
+}
+
+inline cudaStream_t S0(unb_ctx *ctx) { return ctx->lane[0].stream; }
+
+int h2d(unb_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t s)
+{
+    if (!bytes) return UNB_OK;
+    UNB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    ctx->h2d_bytes += (long long)bytes;
+    return UNB_OK;
+}
+int d2h(unb_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t s)
+{
+    if (!bytes) return UNB_OK;
+    UNB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += (long long)bytes;
+    return UNB_OK;
+}
+
+bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+int check_ctx(unb_ctx *ctx)
+{
+    if (!ctx) return UNB_ERR_ARG;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return unb_fail(ctx, UNB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return UNB_OK;
+}
+
+int stat_reset(unb_ctx *ctx, cudaStream_t s)
+{
+    UNB_TRY(unb_reserve(ctx, ctx->stat, sizeof(unsigned long long)));
+    UNB_CUDA(ctx, cudaMemsetAsync(ctx->stat.p, 0, sizeof(unsigned long long), s));
+    return UNB_OK;
+}
+int stat_fetch(unb_ctx *ctx, cudaStream_t s)
+{
+    unsigned long long v = 0;
+    UNB_CUDA(ctx, cudaMemcpyAsync(&v, ctx->stat.p, sizeof(v), cudaMemcpyDeviceToHost, s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->last_rechecks = (long long)v;
+    return UNB_OK;
+}
+
+ScanArgs scan_args_for(const LiveTiles &L)
+{
+    ScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tiles = L.ntiles ? (const double *)L.tiles.p : nullptr;
+    a.live_rows = (const double *)L.rows.p;
+    a.n_live = (int)L.n;
+    a.tile_n = (int)L.tile_n;
+    a.d = (int)L.d;
+    a.dr = (int)L.dr;
+    a.kappa = unb_kappa(L.d);
+    a.namax_bits = (const unsigned long long *)L.namax.p;
+    return a;
+}
+
+// upload a live block into L and build its tiles
+int live_from_host(unb_ctx *ctx, LiveTiles &L, const double *rows, size_t n, size_t d,
+                   cudaStream_t s)
+{
+    UNB_TRY(unb_reserve(ctx, L.rows, (n ? n : 1) * d * sizeof(double)));
+    UNB_TRY(h2d(ctx, L.rows.p, rows, n * d * sizeof(double), s));
+    return unb_live_build(ctx, L, (const double *)L.rows.p, n, d, s);
+}
+
+int check_dims(unb_ctx *ctx, size_t n, size_t d)
+{
+    if (d == 0) return unb_fail(ctx, UNB_ERR_ARG, "ndim must be >= 1");
+    if (d > (1u << 20)) return unb_fail(ctx, UNB_ERR_ARG, "ndim too large");
+    if (n > 0x7fffffffULL) return unb_fail(ctx, UNB_ERR_ARG, "too many rows (max 2^31-1 per call)");
+    return UNB_OK;
+}
+
+// generic host-buffer pair scan against an already built live block
+int scan_host(unb_ctx *ctx, LiveTiles &L, int mode, const double *bpts, size_t nb, double r2,
+              long long *out_idx_host, double *out_rows_host, double *out_max_host)
+{
+    Lane &ln = ctx->lane[0];
+    cudaStream_t s = ln.stream;
+    const size_t d = L.d;
+    UNB_TRY(unb_live_set_h(ctx, L, mode == SCAN_MIN ? HMODE_MIN : HMODE_THRESH, r2, s));
+    UNB_TRY(unb_reserve(ctx, ln.cand, nb * d * sizeof(double)));
+    UNB_TRY(h2d(ctx, ln.cand.p, bpts, nb * d * sizeof(double), s));
+    UNB_TRY(stat_reset(ctx, s));
+    ScanArgs a = scan_args_for(L);
+    a.cand = (const double *)ln.cand.p;
+    a.n_items = (long long)nb;
+    a.r2 = r2;
+    a.stat_rechecks = (unsigned long long *)ctx->stat.p;
+    if (mode == SCAN_FIND || mode == SCAN_COUNT) {
+        UNB_TRY(unb_reserve(ctx, ln.idx, nb * sizeof(long long)));
+        a.out_idx = (long long *)ln.idx.p;
+    } else if (mode == SCAN_SUBTRACT) {
+        UNB_TRY(unb_reserve(ctx, ln.tcand, nb * d * sizeof(double)));
+        a.out_rows = (double *)ln.tcand.p;
+    } else {
+        UNB_TRY(unb_reserve(ctx, ctx->aux0, sizeof(unsigned long long)));
+        UNB_CUDA(ctx, cudaMemsetAsync(ctx->aux0.p, 0, sizeof(unsigned long long), s));
+        a.out_round_max = (unsigned long long *)ctx->aux0.p;
+    }
+    UNB_TRY(unb_launch_scan(ctx, mode, a, 1, s));
+    if (mode == SCAN_FIND || mode == SCAN_COUNT)
+        UNB_TRY(d2h(ctx, out_idx_host, ln.idx.p, nb * sizeof(long long), s));
+    else if (mode == SCAN_SUBTRACT)
+        UNB_TRY(d2h(ctx, out_rows_host, ln.tcand.p, nb * d * sizeof(double), s));
+    else
+        UNB_TRY(d2h(ctx, out_max_host, ctx->aux0.p, sizeof(double), s));
+    return stat_fetch(ctx, s);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+extern "C" int unb_abi_version(void) { return UNB_ABI_VERSION; }
+
+extern "C" int unb_ctx_create(int device, unb_ctx **out)
+{
+    if (!out) return UNB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return UNB_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return UNB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return UNB_ERR_CUDA;
+    if (prop.major != 10) {
+        fprintf(stderr, "ultranest_b200: device %d is sm_%d%d; this library is built for sm_100a only\n",
+                device, prop.major, prop.minor);
+        return UNB_ERR_CUDA;
+    }
+    unb_ctx *ctx = new (std::nothrow) unb_ctx();
+    if (!ctx) return UNB_ERR_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 2; i++) {
+        Lane &ln = ctx->lane[i];
+        if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return UNB_ERR_CUDA;
+        }
+    }
+    *out = ctx;
+    return UNB_OK;
+}
+
+extern "C" int unb_ctx_destroy(unb_ctx *ctx)
+{
+    if (!ctx) return UNB_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        Lane &ln = ctx->lane[i];
+        free_dev(ln.cand); free_dev(ln.tcand); free_dev(ln.items); free_dev(ln.counter);
+        free_dev(ln.mask); free_dev(ln.idx); free_dev(ln.like);
+        free_pin(ln.pin_in); free_pin(ln.pin_mask); free_pin(ln.pin_like); free_pin(ln.pin_idx);
+        if (ln.ev_in) cudaEventDestroy(ln.ev_in);
+        if (ln.ev_done) cudaEventDestroy(ln.ev_done);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+    }
+    free_live(ctx->region.live);
+    free_live(ctx->scratch_live);
+    free_dev(ctx->region.layer_shift); free_dev(ctx->region.layer_mat);
+    free_dev(ctx->region.ell_center); free_dev(ctx->region.ell_invcov);
+    free_dev(ctx->aux0); free_dev(ctx->aux1); free_dev(ctx->aux2); free_dev(ctx->aux3);
+    free_dev(ctx->stat); free_dev(ctx->lparams);
+    free_dev(ctx->boot_rows); free_dev(ctx->boot_u); free_dev(ctx->boot_tiles);
+    free_dev(ctx->boot_idx); free_dev(ctx->boot_meta); free_dev(ctx->boot_out);
+    free_dev(ctx->boot_ell);
+    free_pin(ctx->pin_small);
+    delete ctx;
+    return UNB_OK;
+}
+
+extern "C" const char *unb_last_error(const unb_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int unb_ctx_set_option(unb_ctx *ctx, int option, int64_t value)
+{
+    if (!ctx) return UNB_ERR_ARG;
+    switch (option) {
+    case UNB_OPT_EXACT_ONLY: ctx->exact_only = value ? 1 : 0; return UNB_OK;
+    case UNB_OPT_CHUNK_ROWS: ctx->chunk_rows = value > 0 ? value : 0; return UNB_OK;
+    default: return unb_fail(ctx, UNB_ERR_ARG, "unknown option %d", option);
+    }
+}
+
+extern "C" int unb_ctx_get_stat(unb_ctx *ctx, int stat, int64_t *value)
+{
+    if (!ctx || !value) return UNB_ERR_ARG;
+    switch (stat) {
+    case UNB_STAT_KERNEL_LAUNCHES: *value = ctx->launches; return UNB_OK;
+    case UNB_STAT_RECHECKS: *value = ctx->last_rechecks; return UNB_OK;
+    case UNB_STAT_H2D_BYTES: *value = ctx->h2d_bytes; return UNB_OK;
+    case UNB_STAT_D2H_BYTES: *value = ctx->d2h_bytes; return UNB_OK;
+    default: return unb_fail(ctx, UNB_ERR_ARG, "unknown stat %d", stat);
+    }
+}
+
+extern "C" int unb_ctx_synchronize(unb_ctx *ctx)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+    return UNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stateless scans
+// ---------------------------------------------------------------------------------------
+extern "C" int unb_find_nearby(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
+                               size_t nb, size_t ndim, double radiussq, int64_t *nnearby)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, na > nb ? na : nb, ndim));
+    if (nb == 0) return UNB_OK;
+    if (!bpts || !nnearby || (na && !apts)) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (na == 0) {   // no members: every entry is -1 (mlfriends.pyx:176)
+        for (size_t j = 0; j < nb; j++) nnearby[j] = -1;
+        return UNB_OK;
+    }
+    UNB_TRY(live_from_host(ctx, ctx->scratch_live, apts, na, ndim, S0(ctx)));
+    return scan_host(ctx, ctx->scratch_live, SCAN_FIND, bpts, nb, radiussq,
+                     (long long *)nnearby, nullptr, nullptr);
+}
+
+extern "C" int unb_count_nearby(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
+                                size_t nb, size_t ndim, double radiussq, int64_t *nnearby)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, na > nb ? na : nb, ndim));
+    if (nb == 0) return UNB_OK;
+    if (!bpts || !nnearby || (na && !apts)) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (na == 0) {
+        for (size_t j = 0; j < nb; j++) nnearby[j] = 0;
+        return UNB_OK;
+    }
+    UNB_TRY(live_from_host(ctx, ctx->scratch_live, apts, na, ndim, S0(ctx)));
+    return scan_host(ctx, ctx->scratch_live, SCAN_COUNT, bpts, nb, radiussq,
+                     (long long *)nnearby, nullptr, nullptr);
+}
+
+extern "C" int unb_subtract_nearby(unb_ctx *ctx, const double *apts, size_t n, size_t ndim,
+                                   double radiussq, double *bpts_out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, n, ndim));
+    if (n == 0) return UNB_OK;
+    if (!apts || !bpts_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    UNB_TRY(live_from_host(ctx, ctx->scratch_live, apts, n, ndim, S0(ctx)));
+    return scan_host(ctx, ctx->scratch_live, SCAN_SUBTRACT, apts, n, radiussq, nullptr, bpts_out,
+                     nullptr);
+}
+
+extern "C" int unb_compute_maxradiussq(unb_ctx *ctx, const double *apts, size_t na,
+                                       const double *bpts, size_t nb, size_t ndim,
+                                       double *maxd_out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, na > nb ? na : nb, ndim));
+    if (!maxd_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (nb == 0) {   // maxd stays 0 (mlfriends.pyx:209)
+        *maxd_out = 0.0;
+        return UNB_OK;
+    }
+    if (na == 0) {   // mind stays 1e300 for every b; (float)1e300 = inf
+        *maxd_out = (double)(float)1e300;
+        return UNB_OK;
+    }
+    UNB_TRY(live_from_host(ctx, ctx->scratch_live, apts, na, ndim, S0(ctx)));
+    double maxd = 0.0;
+    UNB_TRY(scan_host(ctx, ctx->scratch_live, SCAN_MIN, bpts, nb, 0.0, nullptr, nullptr, &maxd));
+    *maxd_out = (double)(float)maxd;   // C `float` return of the reference (mlfriends.pyx:188)
+    return UNB_OK;
+}
+
+extern "C" int unb_mean_pair_distance(unb_ctx *ctx, const double *pts, const int64_t *clusterids,
+                                      size_t n, size_t ndim, double *out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, n, ndim));
+    if (!out || (n && (!pts || !clusterids))) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    cudaStream_t s = S0(ctx);
+    UNB_TRY(unb_reserve(ctx, ctx->aux0, n * ndim * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->aux1, n * sizeof(long long)));
+    UNB_TRY(unb_reserve(ctx, ctx->aux2, n * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->aux3, n * sizeof(long long)));
+    UNB_TRY(h2d(ctx, ctx->aux0.p, pts, n * ndim * sizeof(double), s));
+    UNB_TRY(h2d(ctx, ctx->aux1.p, clusterids, n * sizeof(long long), s));
+    UNB_TRY(unb_launch_pairdist(ctx, (const double *)ctx->aux0.p, (const long long *)ctx->aux1.p,
+                                (int)n, (int)ndim, (double *)ctx->aux2.p, (long long *)ctx->aux3.p, s));
+    std::vector<double> ps(n);
+    std::vector<long long> pc(n);
+    UNB_TRY(d2h(ctx, ps.data(), ctx->aux2.p, n * sizeof(double), s));
+    UNB_TRY(d2h(ctx, pc.data(), ctx->aux3.p, n * sizeof(long long), s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    double total = 0.0;
+    long long npairs = 0;
+    for (size_t j = 0; j < n; j++) {   // final fold of the per-row device partials
+        total += ps[j];
+        npairs += pc[j];
+    }
+    *out = total / (double)npairs;
+    return UNB_OK;
+}
+
+extern "C" int unb_inside_ellipsoid(unb_ctx *ctx, const double *points, size_t m, size_t ndim,
+                                    const double *center, const double *invcov,
+                                    double square_radius, uint8_t *mask)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, m, ndim));
+    if (m == 0) return UNB_OK;
+    if (!points || !center || !invcov || !mask) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    Lane &ln = ctx->lane[0];
+    cudaStream_t s = ln.stream;
+    UNB_TRY(unb_reserve(ctx, ln.cand, m * ndim * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ln.mask, m));
+    UNB_TRY(unb_reserve(ctx, ctx->aux0, ndim * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->aux1, ndim * ndim * sizeof(double)));
+    UNB_TRY(h2d(ctx, ln.cand.p, points, m * ndim * sizeof(double), s));
+    UNB_TRY(h2d(ctx, ctx->aux0.p, center, ndim * sizeof(double), s));
+    UNB_TRY(h2d(ctx, ctx->aux1.p, invcov, ndim * ndim * sizeof(double), s));
+    PrepArgs p;
+    memset(&p, 0, sizeof(p));
+    p.pts = (const double *)ln.cand.p;
+    p.m = (long long)m;
+    p.d = (int)ndim;
+    p.center = (const double *)ctx->aux0.p;
+    p.invcov = (const double *)ctx->aux1.p;
+    p.r2 = square_radius;
+    p.mask = (unsigned char *)ln.mask.p;
+    p.layer_kind = -1;
+    UNB_TRY(unb_launch_prep(ctx, p, s));
+    UNB_TRY(d2h(ctx, mask, ln.mask.p, m, s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    return UNB_OK;
+}
+
+namespace {
+int transform_host(unb_ctx *ctx, int kind, bool inverse, const double *in, size_t m, size_t d,
+                   const double *shift, size_t shift_n, const double *mat, size_t mat_n,
+                   double *out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, m, d));
+    if (m == 0) return UNB_OK;
+    if (!in || !out || !shift || !mat) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    Lane &ln = ctx->lane[0];
+    cudaStream_t s = ln.stream;
+    UNB_TRY(unb_reserve(ctx, ln.cand, m * d * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ln.tcand, m * d * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->aux0, shift_n * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->aux1, mat_n * sizeof(double)));
+    UNB_TRY(h2d(ctx, ln.cand.p, in, m * d * sizeof(double), s));
+    UNB_TRY(h2d(ctx, ctx->aux0.p, shift, shift_n * sizeof(double), s));
+    UNB_TRY(h2d(ctx, ctx->aux1.p, mat, mat_n * sizeof(double), s));
+    UNB_TRY(unb_launch_transform(ctx, kind, inverse, (const double *)ln.cand.p, (long long)m, (int)d,
+                                 (const double *)ctx->aux0.p, (const double *)ctx->aux1.p,
+                                 (double *)ln.tcand.p, s));
+    UNB_TRY(d2h(ctx, out, ln.tcand.p, m * d * sizeof(double), s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    return UNB_OK;
+}
+}  // namespace
+
+extern "C" int unb_transform_scaling(unb_ctx *ctx, const double *w, size_t m, size_t ndim,
+                                     const double *mean, const double *std, double *out)
+{
+    return transform_host(ctx, UNB_LAYER_SCALING, false, w, m, ndim, mean, ndim, std, ndim, out);
+}
+extern "C" int unb_untransform_scaling(unb_ctx *ctx, const double *ww, size_t m, size_t ndim,
+                                       const double *mean, const double *std, double *out)
+{
+    return transform_host(ctx, UNB_LAYER_SCALING, true, ww, m, ndim, mean, ndim, std, ndim, out);
+}
+extern "C" int unb_transform_affine(unb_ctx *ctx, const double *w, size_t m, size_t ndim,
+                                    const double *ctr, const double *T, double *out)
+{
+    return transform_host(ctx, UNB_LAYER_AFFINE, false, w, m, ndim, ctr, ndim, T, ndim * ndim, out);
+}
+extern "C" int unb_untransform_affine(unb_ctx *ctx, const double *ww, size_t m, size_t ndim,
+                                      const double *ctr, const double *invT, double *out)
+{
+    return transform_host(ctx, UNB_LAYER_AFFINE, true, ww, m, ndim, ctr, ndim, invT, ndim * ndim, out);
+}
+
+// ---------------------------------------------------------------------------------------
+// stateful region
+// ---------------------------------------------------------------------------------------
+extern "C" int unb_region_sync_live(unb_ctx *ctx, const double *unormed, size_t n, size_t ndim,
+                                    int64_t *rows_changed)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, n, ndim));
+    if (!unormed || n == 0) return unb_fail(ctx, UNB_ERR_ARG, "empty live block");
+    RegionState &R = ctx->region;
+    cudaStream_t s = S0(ctx);
+    const size_t rowb = ndim * sizeof(double);
+    bool full = !R.live.valid || R.live.n != n || R.live.d != ndim || R.snapshot.size() != n * ndim;
+    std::vector<int> changed;
+    if (!full) {
+        const char *cur = (const char *)unormed;
+        const char *old = (const char *)R.snapshot.data();
+        if (memcmp(cur, old, n * rowb) != 0) {
+            for (size_t i = 0; i < n; i++)
+                if (memcmp(cur + i * rowb, old + i * rowb, rowb) != 0) changed.push_back((int)i);
+            if (changed.size() > n / 4) full = true;
+        }
+    }
+    if (full) {
+        // both lanes may still read the old mirror
+        UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+        R.snapshot.assign(unormed, unormed + n * ndim);
+        UNB_TRY(live_from_host(ctx, R.live, unormed, n, ndim, s));
+        UNB_CUDA(ctx, cudaStreamSynchronize(s));
+        if (rows_changed) *rows_changed = (int64_t)n;
+        return UNB_OK;
+    }
+    if (!changed.empty()) {
+        UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+        const size_t k = changed.size();
+        UNB_TRY(unb_reserve_pinned(ctx, ctx->pin_small, k * (rowb + sizeof(int))));
+        char *stage = (char *)ctx->pin_small.p;
+        int *idx_stage = (int *)(stage + k * rowb);
+        for (size_t r = 0; r < k; r++) {
+            const size_t i = (size_t)changed[r];
+            memcpy(stage + r * rowb, unormed + i * ndim, rowb);
+            memcpy(R.snapshot.data() + i * ndim, unormed + i * ndim, rowb);
+            idx_stage[r] = changed[r];
+            UNB_TRY(h2d(ctx, (char *)R.live.rows.p + i * rowb, stage + r * rowb, rowb, s));
+        }
+        UNB_TRY(unb_reserve(ctx, ctx->aux3, k * sizeof(int)));
+        UNB_TRY(h2d(ctx, ctx->aux3.p, idx_stage, k * sizeof(int), s));
+        UNB_TRY(unb_live_update_rows(ctx, R.live, (const int *)ctx->aux3.p, k, s));
+        UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    if (rows_changed) *rows_changed = (int64_t)changed.size();
+    return UNB_OK;
+}
+
+extern "C" int unb_region_set_layer(unb_ctx *ctx, int kind, const double *shift, const double *mat,
+                                    size_t ndim)
+{
+    UNB_TRY(check_ctx(ctx));
+    RegionState &R = ctx->region;
+    cudaStream_t s = S0(ctx);
+    if (kind != UNB_LAYER_IDENTITY && kind != UNB_LAYER_SCALING && kind != UNB_LAYER_AFFINE)
+        return unb_fail(ctx, UNB_ERR_ARG, "unknown layer kind %d", kind);
+    if (kind != UNB_LAYER_IDENTITY) {
+        if (!shift || !mat || ndim == 0) return unb_fail(ctx, UNB_ERR_ARG, "null layer parameters");
+        const size_t mat_n = kind == UNB_LAYER_AFFINE ? ndim * ndim : ndim;
+        if (R.layer_kind == kind && R.layer_d == ndim && R.layer_shift_h.size() == ndim &&
+            R.layer_mat_h.size() == mat_n &&
+            memcmp(R.layer_shift_h.data(), shift, ndim * sizeof(double)) == 0 &&
+            memcmp(R.layer_mat_h.data(), mat, mat_n * sizeof(double)) == 0)
+            return UNB_OK;   // unchanged since the last call
+        R.layer_shift_h.assign(shift, shift + ndim);
+        R.layer_mat_h.assign(mat, mat + mat_n);
+        UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+        UNB_TRY(unb_reserve(ctx, R.layer_shift, ndim * sizeof(double)));
+        UNB_TRY(unb_reserve(ctx, R.layer_mat, mat_n * sizeof(double)));
+        UNB_TRY(h2d(ctx, R.layer_shift.p, shift, ndim * sizeof(double), s));
+        UNB_TRY(h2d(ctx, R.layer_mat.p, mat, mat_n * sizeof(double), s));
+        UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    R.layer_kind = kind;
+    R.layer_d = ndim;
+    return UNB_OK;
+}
+
+extern "C" int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, const double *invcov,
+                                        double enlarge, size_t ndim)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!center || !invcov || ndim == 0) return unb_fail(ctx, UNB_ERR_ARG, "null ellipsoid");
+    RegionState &R = ctx->region;
+    cudaStream_t s = S0(ctx);
+    R.enlarge = enlarge;
+    if (R.have_ellipsoid && R.ell_d == ndim && R.ell_center_h.size() == ndim &&
+        memcmp(R.ell_center_h.data(), center, ndim * sizeof(double)) == 0 &&
+        memcmp(R.ell_invcov_h.data(), invcov, ndim * ndim * sizeof(double)) == 0)
+        return UNB_OK;   // unchanged since the last call
+    R.ell_center_h.assign(center, center + ndim);
+    R.ell_invcov_h.assign(invcov, invcov + ndim * ndim);
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+    UNB_TRY(unb_reserve(ctx, R.ell_center, ndim * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, R.ell_invcov, ndim * ndim * sizeof(double)));
+    UNB_TRY(h2d(ctx, R.ell_center.p, center, ndim * sizeof(double), s));
+    UNB_TRY(h2d(ctx, R.ell_invcov.p, invcov, ndim * ndim * sizeof(double), s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    R.ell_d = ndim;
+    R.enlarge = enlarge;
+    R.have_ellipsoid = true;
+    return UNB_OK;
+}
+
+extern "C" int unb_region_set_radius(unb_ctx *ctx, double maxradiussq)
+{
+    if (!ctx) return UNB_ERR_ARG;
+    ctx->region.r2 = maxradiussq;
+    ctx->region.have_radius = true;
+    return UNB_OK;
+}
+
+namespace {
+
+int region_ready(unb_ctx *ctx, bool need_ellipsoid)
+{
+    RegionState &R = ctx->region;
+    if (!R.live.valid) return unb_fail(ctx, UNB_ERR_STATE, "region live block not set");
+    if (!R.have_radius) return unb_fail(ctx, UNB_ERR_STATE, "region radius not set");
+    if (need_ellipsoid) {
+        if (!R.have_ellipsoid) return unb_fail(ctx, UNB_ERR_STATE, "region ellipsoid not set");
+        if (R.ell_d != R.live.d) return unb_fail(ctx, UNB_ERR_STATE, "ellipsoid/live ndim mismatch");
+        if (R.layer_kind != UNB_LAYER_IDENTITY && R.layer_d != R.live.d)
+            return unb_fail(ctx, UNB_ERR_STATE, "layer/live ndim mismatch");
+    }
+    return UNB_OK;
+}
+
+// enqueue MLFriends.inside (+ optional likelihood) for device-resident rows on lane `ln`
+int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev, size_t m,
+                   unsigned char *mask_dev, long long *idx_dev, double *like_dev,
+                   int loglike_kind)
+{
+    RegionState &R = ctx->region;
+    const size_t d = R.live.d;
+    UNB_TRY(unb_reserve(ctx, ln.tcand, m * d * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ln.items, m * sizeof(int)));
+    UNB_TRY(unb_reserve(ctx, ln.counter, sizeof(int)));
+    UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, sizeof(int), s));
+    if (idx_dev) UNB_CUDA(ctx, cudaMemsetAsync(idx_dev, 0xff, m * sizeof(long long), s));
+    PrepArgs p;
+    memset(&p, 0, sizeof(p));
+    p.pts = pts_dev;
+    p.m = (long long)m;
+    p.d = (int)d;
+    p.center = (const double *)R.ell_center.p;
+    p.invcov = (const double *)R.ell_invcov.p;
+    p.r2 = R.enlarge;
+    p.mask = mask_dev;
+    p.layer_kind = R.layer_kind;
+    p.shift = (const double *)R.layer_shift.p;
+    p.mat = (const double *)R.layer_mat.p;
+    p.tcand = (double *)ln.tcand.p;
+    p.items = (int *)ln.items.p;
+    p.n_items = (int *)ln.counter.p;
+    UNB_TRY(unb_launch_prep(ctx, p, s));
+    ScanArgs a = scan_args_for(R.live);
+    a.cand = (const double *)ln.tcand.p;
+    a.out_row_idx = (const int *)ln.items.p;
+    a.n_items_dev = (const int *)ln.counter.p;
+    a.n_items = (long long)m;
+    a.r2 = R.r2;
+    a.out_mask = mask_dev;
+    a.out_idx = idx_dev;
+    UNB_TRY(unb_launch_scan(ctx, SCAN_FIND, a, 1, s));
+    if (like_dev && loglike_kind != UNB_LOGLIKE_NONE)
+        UNB_TRY(unb_launch_loglike(ctx, loglike_kind, pts_dev, (int)d, (long long)m, like_dev,
+                                   mask_dev, (const double *)ctx->lparams.p, s));
+    return UNB_OK;
+}
+
+void lane_flush(Lane &ln)
+{
+    if (!ln.pend_rows) return;
+    cudaEventSynchronize(ln.ev_done);
+    if (ln.pend_mask) memcpy(ln.pend_mask, ln.pin_mask.p, ln.pend_rows);
+    if (ln.pend_like) memcpy(ln.pend_like, ln.pin_like.p, ln.pend_rows * sizeof(double));
+    if (ln.pend_idx) memcpy(ln.pend_idx, ln.pin_idx.p, ln.pend_rows * sizeof(long long));
+    ln.pend_rows = 0;
+    ln.pend_mask = nullptr;
+    ln.pend_like = nullptr;
+    ln.pend_idx = nullptr;
+}
+
+int upload_lparams(unb_ctx *ctx, int kind, const double *lparams, size_t d, cudaStream_t s)
+{
+    if (kind == UNB_LOGLIKE_GAUSS) {
+        if (!lparams) return unb_fail(ctx, UNB_ERR_ARG, "gaussian likelihood needs parameters");
+        UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
+        UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+        UNB_TRY(unb_reserve(ctx, ctx->lparams, (d + 2) * sizeof(double)));
+        UNB_TRY(h2d(ctx, ctx->lparams.p, lparams, (d + 2) * sizeof(double), s));
+        UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    } else if (kind != UNB_LOGLIKE_NONE && kind != UNB_LOGLIKE_EGGBOX && kind != UNB_LOGLIKE_ROSENBROCK) {
+        return unb_fail(ctx, UNB_ERR_ARG, "unknown likelihood kind %d", kind);
+    }
+    return UNB_OK;
+}
+
+// chunked, double-buffered host pipeline: H2D(c+1) overlaps kernels(c) and D2H(c)
+int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_t *idx_out,
+                double *like, int loglike_kind)
+{
+    RegionState &R = ctx->region;
+    const size_t d = R.live.d;
+    const size_t rowb = d * sizeof(double);
+    UNB_TRY(unb_live_set_h(ctx, R.live, HMODE_THRESH, R.r2, S0(ctx)));
+    UNB_CUDA(ctx, cudaStreamSynchronize(S0(ctx)));
+    size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 17);
+    if (chunk > m) chunk = m;
+    const bool src_pinned = host_is_pinned(pts);
+    const bool mask_pinned = host_is_pinned(mask);
+    const bool like_pinned = like ? host_is_pinned(like) : true;
+    const bool idx_pinned = idx_out ? host_is_pinned(idx_out) : true;
+    int rc = UNB_OK;
+    size_t c = 0;
+    for (size_t off = 0; off < m && rc == UNB_OK; off += chunk, c++) {
+        const size_t rows = std::min(chunk, m - off);
+        Lane &ln = ctx->lane[c & 1];
+        cudaStream_t s = ln.stream;
+        lane_flush(ln);
+        auto body = [&]() -> int {
+            UNB_TRY(unb_reserve(ctx, ln.cand, chunk * rowb));
+            UNB_TRY(unb_reserve(ctx, ln.mask, chunk));
+            if (idx_out) UNB_TRY(unb_reserve(ctx, ln.idx, chunk * sizeof(long long)));
+            if (like) UNB_TRY(unb_reserve(ctx, ln.like, chunk * sizeof(double)));
+            if (src_pinned) {
+                UNB_TRY(h2d(ctx, ln.cand.p, pts + off * d, rows * rowb, s));
+            } else {
+                UNB_TRY(unb_reserve_pinned(ctx, ln.pin_in, chunk * rowb));
+                UNB_CUDA(ctx, cudaEventSynchronize(ln.ev_in));
+                memcpy(ln.pin_in.p, pts + off * d, rows * rowb);
+                UNB_TRY(h2d(ctx, ln.cand.p, ln.pin_in.p, rows * rowb, s));
+                UNB_CUDA(ctx, cudaEventRecord(ln.ev_in, s));
+            }
+            UNB_TRY(enqueue_inside(ctx, ln, s, (const double *)ln.cand.p, rows,
+                                   (unsigned char *)ln.mask.p,
+                                   idx_out ? (long long *)ln.idx.p : nullptr,
+                                   like ? (double *)ln.like.p : nullptr, loglike_kind));
+            ln.pend_rows = 0;
+            if (mask_pinned) {
+                UNB_TRY(d2h(ctx, mask + off, ln.mask.p, rows, s));
+            } else {
+                UNB_TRY(unb_reserve_pinned(ctx, ln.pin_mask, chunk));
+                UNB_TRY(d2h(ctx, ln.pin_mask.p, ln.mask.p, rows, s));
+                ln.pend_mask = mask + off;
+                ln.pend_rows = rows;
+            }
+            if (like) {
+                if (like_pinned) {
+                    UNB_TRY(d2h(ctx, like + off, ln.like.p, rows * sizeof(double), s));
+                } else {
+                    UNB_TRY(unb_reserve_pinned(ctx, ln.pin_like, chunk * sizeof(double)));
+                    UNB_TRY(d2h(ctx, ln.pin_like.p, ln.like.p, rows * sizeof(double), s));
+                    ln.pend_like = like + off;
+                    ln.pend_rows = rows;
+                }
+            }
+            if (idx_out) {
+                if (idx_pinned) {
+                    UNB_TRY(d2h(ctx, idx_out + off, ln.idx.p, rows * sizeof(long long), s));
+                } else {
+                    UNB_TRY(unb_reserve_pinned(ctx, ln.pin_idx, chunk * sizeof(long long)));
+                    UNB_TRY(d2h(ctx, ln.pin_idx.p, ln.idx.p, rows * sizeof(long long), s));
+                    ln.pend_idx = (long long *)idx_out + off;
+                    ln.pend_rows = rows;
+                }
+            }
+            UNB_CUDA(ctx, cudaEventRecord(ln.ev_done, s));
+            return UNB_OK;
+        };
+        rc = body();
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaStreamSynchronize(ctx->lane[i].stream);
+        lane_flush(ctx->lane[i]);
+    }
+    if (rc == UNB_OK) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return unb_fail(ctx, UNB_ERR_CUDA, "inside pipeline: %s", cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int unb_region_inside(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
+                                 int64_t *idx_out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(region_ready(ctx, true));
+    if (m == 0) return UNB_OK;
+    if (!pts || !mask) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    return inside_host(ctx, pts, m, mask, idx_out, nullptr, UNB_LOGLIKE_NONE);
+}
+
+extern "C" int unb_region_inside_loglike(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
+                                         double *like, int loglike_kind, const double *lparams)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(region_ready(ctx, true));
+    if (m == 0) return UNB_OK;
+    if (!pts || !mask || !like) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    UNB_TRY(upload_lparams(ctx, loglike_kind, lparams, ctx->region.live.d, S0(ctx)));
+    return inside_host(ctx, pts, m, mask, nullptr, like, loglike_kind);
+}
+
+extern "C" int unb_region_inside_dev(unb_ctx *ctx, const double *pts_dev, size_t m,
+                                     uint8_t *mask_dev, void *stream)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(region_ready(ctx, true));
+    if (m == 0) return UNB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
+    UNB_TRY(unb_live_set_h(ctx, ctx->region.live, HMODE_THRESH, ctx->region.r2, s));
+    return enqueue_inside(ctx, ctx->lane[0], s, pts_dev, m, mask_dev, nullptr, nullptr,
+                          UNB_LOGLIKE_NONE);
+}
+
+extern "C" int unb_region_inside_loglike_dev(unb_ctx *ctx, const double *pts_dev, size_t m,
+                                             uint8_t *mask_dev, double *like_dev, int loglike_kind,
+                                             const double *lparams, void *stream)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(region_ready(ctx, true));
+    if (m == 0) return UNB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
+    if (lparams) UNB_TRY(upload_lparams(ctx, loglike_kind, lparams, ctx->region.live.d, s));
+    UNB_TRY(unb_live_set_h(ctx, ctx->region.live, HMODE_THRESH, ctx->region.r2, s));
+    return enqueue_inside(ctx, ctx->lane[0], s, pts_dev, m, mask_dev, nullptr, like_dev,
+                          loglike_kind);
+}
+
+extern "C" int unb_region_find_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(region_ready(ctx, false));
+    if (m == 0) return UNB_OK;
+    if (!tpts || !nnearby) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    return scan_host(ctx, ctx->region.live, SCAN_FIND, tpts, m, ctx->region.r2,
+                     (long long *)nnearby, nullptr, nullptr);
+}
+
+extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, size_t m,
+                                          int64_t *nnearby_dev, uint8_t *mask_dev, void *stream)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(region_ready(ctx, false));
+    if (m == 0) return UNB_OK;
+    if (!tpts_dev || (!nnearby_dev && !mask_dev)) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
+    UNB_TRY(unb_live_set_h(ctx, ctx->region.live, HMODE_THRESH, ctx->region.r2, s));
+    ScanArgs a = scan_args_for(ctx->region.live);
+    a.cand = tpts_dev;
+    a.n_items = (long long)m;
+    a.r2 = ctx->region.r2;
+    a.out_idx = (long long *)nnearby_dev;
+    a.out_mask = mask_dev;
+    return unb_launch_scan(ctx, SCAN_FIND, a, 1, s);
+}
+
+extern "C" int unb_region_count_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(region_ready(ctx, false));
+    if (m == 0) return UNB_OK;
+    if (!tpts || !nnearby) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    return scan_host(ctx, ctx->region.live, SCAN_COUNT, tpts, m, ctx->region.r2,
+                     (long long *)nnearby, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------
+// bootstrap
+// ---------------------------------------------------------------------------------------
+extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const double *u, size_t n,
+                                    size_t ndim, const uint8_t *selected, size_t nrounds,
+                                    size_t round_lo, size_t round_hi, const double *ctrs,
+                                    const double *invcovs, double *maxd_out, double *f_out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, n, ndim));
+    const bool want_d = unormed && maxd_out;
+    const bool want_f = u && ctrs && invcovs && f_out;
+    if (!selected || n == 0 || (!want_d && !want_f))
+        return unb_fail(ctx, UNB_ERR_ARG, "null pointer / empty live block");
+    if (round_hi > nrounds) round_hi = nrounds;
+    if (round_lo >= round_hi) return UNB_OK;
+    cudaStream_t s = S0(ctx);
+    const size_t d = ndim;
+
+    // host: index lists of the active rounds (selection masks come from the host RNG in the
+    // reference's order; rounds with all/none selected are skipped like mlfriends.pyx:1048-1049)
+    std::vector<int> round_of;          // active slot -> round
+    std::vector<int> idxA, idxB, offA, offB, nA, nB;
+    for (size_t r = round_lo; r < round_hi; r++) {
+        const uint8_t *sel = selected + r * n;
+        size_t ca = 0;
+        for (size_t i = 0; i < n; i++) ca += sel[i] ? 1 : 0;
+        if (ca == 0 || ca == n) {
+            if (want_d) maxd_out[r] = 0.0;
+            if (want_f) f_out[r] = 0.0;
+            continue;
+        }
+        round_of.push_back((int)r);
+        offA.push_back((int)idxA.size());
+        offB.push_back((int)idxB.size());
+        nA.push_back((int)ca);
+        nB.push_back((int)(n - ca));
+        for (size_t i = 0; i < n; i++) {
+            if (sel[i]) idxA.push_back((int)i);
+            else idxB.push_back((int)i);
+        }
+    }
+    const int R = (int)round_of.size();
+    if (R == 0) return UNB_OK;
+
+    // device: rows, index lists, meta
+    if (want_d) {
+        UNB_TRY(unb_reserve(ctx, ctx->boot_rows, n * d * sizeof(double)));
+        UNB_TRY(h2d(ctx, ctx->boot_rows.p, unormed, n * d * sizeof(double), s));
+    }
+    const size_t nidx = idxA.size() + idxB.size();
+    UNB_TRY(unb_reserve(ctx, ctx->boot_idx, nidx * sizeof(int)));
+    int *dA = (int *)ctx->boot_idx.p;
+    int *dB = dA + idxA.size();
+    UNB_TRY(h2d(ctx, dA, idxA.data(), idxA.size() * sizeof(int), s));
+    UNB_TRY(h2d(ctx, dB, idxB.data(), idxB.size() * sizeof(int), s));
+    UNB_TRY(unb_reserve(ctx, ctx->boot_meta, 4 * (size_t)R * sizeof(int)));
+    int *dOffA = (int *)ctx->boot_meta.p, *dOffB = dOffA + R, *dNA = dOffB + R, *dNB = dNA + R;
+    UNB_TRY(h2d(ctx, dOffA, offA.data(), R * sizeof(int), s));
+    UNB_TRY(h2d(ctx, dOffB, offB.data(), R * sizeof(int), s));
+    UNB_TRY(h2d(ctx, dNA, nA.data(), R * sizeof(int), s));
+    UNB_TRY(h2d(ctx, dNB, nB.data(), R * sizeof(int), s));
+    UNB_TRY(unb_reserve(ctx, ctx->boot_out, 2 * (size_t)R * sizeof(unsigned long long)));
+    UNB_CUDA(ctx, cudaMemsetAsync(ctx->boot_out.p, 0, 2 * (size_t)R * sizeof(unsigned long long), s));
+    unsigned long long *dMax = (unsigned long long *)ctx->boot_out.p;
+    unsigned long long *dF = dMax + R;
+
+    int maxB = 0;
+    for (int r = 0; r < R; r++) maxB = std::max(maxB, nB[r]);
+    UNB_TRY(stat_reset(ctx, s));
+    if (want_d) {
+        // per-round compacted tiles of the selected rows
+        const size_t dr = (d + 3) / 4 * 4;
+        const size_t tile_n = unb_pick_tile_n(d);
+        ScanArgs a;
+        memset(&a, 0, sizeof(a));
+        a.live_rows = (const double *)ctx->boot_rows.p;
+        a.live_idx = dA;
+        a.round_live_off = dOffA;
+        a.d = (int)d;
+        a.dr = (int)dr;
+        a.tile_n = (int)tile_n;
+        a.kappa = unb_kappa(d);
+        a.round_nlive = dNA;
+        a.round_nitems = dNB;
+        a.round_item_off = dOffB;
+        a.cand = (const double *)ctx->boot_rows.p;
+        a.item_idx = dB;
+        a.out_round_max = dMax;
+        a.n_items = maxB;
+        a.stat_rechecks = (unsigned long long *)ctx->stat.p;
+        if (tile_n > 0 && !ctx->exact_only) {
+            const size_t max_tiles = (n + tile_n - 1) / tile_n;
+            const long long stride = (long long)(max_tiles * (dr + 1) * tile_n);
+            UNB_TRY(unb_reserve(ctx, ctx->boot_tiles, (size_t)R * (size_t)stride * sizeof(double)));
+            UNB_TRY(unb_launch_gather_round_tiles(ctx, (const double *)ctx->boot_rows.p, (int)n,
+                                                  (int)d, (int)dr, (int)tile_n, dA, dOffA, dNA, R,
+                                                  stride, (double *)ctx->boot_tiles.p, s));
+            a.tiles = (const double *)ctx->boot_tiles.p;
+            a.round_tile_stride = stride;
+            // max squared norm over ALL rows bounds every round's subset
+            UNB_TRY(unb_live_build(ctx, ctx->scratch_live, (const double *)ctx->boot_rows.p, n, d, s));
+            a.namax_bits = (const unsigned long long *)ctx->scratch_live.namax.p;
+        }
+        UNB_TRY(unb_launch_scan(ctx, SCAN_MIN, a, R, s));
+    }
+
+    if (want_f) {
+        UNB_TRY(unb_reserve(ctx, ctx->boot_u, n * d * sizeof(double)));
+        UNB_TRY(h2d(ctx, ctx->boot_u.p, u, n * d * sizeof(double), s));
+        UNB_TRY(unb_reserve_pinned(ctx, ctx->pin_small, (size_t)R * (d + d * d) * sizeof(double)));
+        double *hc = (double *)ctx->pin_small.p;
+        double *ha = hc + (size_t)R * d;
+        for (int r = 0; r < R; r++) {
+            memcpy(hc + (size_t)r * d, ctrs + (size_t)round_of[r] * d, d * sizeof(double));
+            memcpy(ha + (size_t)r * d * d, invcovs + (size_t)round_of[r] * d * d, d * d * sizeof(double));
+        }
+        UNB_TRY(unb_reserve(ctx, ctx->boot_ell, (size_t)R * (d + d * d) * sizeof(double)));
+        UNB_TRY(h2d(ctx, ctx->boot_ell.p, hc, (size_t)R * (d + d * d) * sizeof(double), s));
+        const double *dC = (const double *)ctx->boot_ell.p;
+        const double *dAinv = dC + (size_t)R * d;
+        UNB_TRY(unb_launch_enlargement_f(ctx, (const double *)ctx->boot_u.p, (int)d, dB, dOffB, dNB,
+                                         maxB, dC, dAinv, R, dF, s));
+    }
+    std::vector<unsigned long long> out(2 * (size_t)R);
+    UNB_TRY(d2h(ctx, out.data(), ctx->boot_out.p, 2 * (size_t)R * sizeof(unsigned long long), s));
+    UNB_TRY(stat_fetch(ctx, s));
+    for (int r = 0; r < R; r++) {
+        if (want_d) {
+            double maxd;
+            memcpy(&maxd, &out[r], sizeof(double));
+            maxd_out[round_of[r]] = (double)(float)maxd;   // C `float` return (mlfriends.pyx:188)
+        }
+        if (want_f) {
+            unsigned long long key = out[R + r];
+            unsigned long long bits = (key >> 63) ? (key & 0x7fffffffffffffffULL) : ~key;
+            double f;
+            memcpy(&f, &bits, sizeof(double));
+            f_out[round_of[r]] = f;
+        }
+    }
+    return UNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// likelihoods
+// ---------------------------------------------------------------------------------------
+namespace {
+int loglike_host(unb_ctx *ctx, int kind, const double *params, size_t d, size_t n, double *like,
+                 const double *lparams)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, n, d));
+    if (n == 0) return UNB_OK;
+    if (!params || !like) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (kind == UNB_LOGLIKE_ROSENBROCK && d < 2) return unb_fail(ctx, UNB_ERR_ARG, "rosenbrock needs ndim >= 2");
+    Lane &ln = ctx->lane[0];
+    cudaStream_t s = ln.stream;
+    UNB_TRY(upload_lparams(ctx, kind, lparams, d, s));
+    UNB_TRY(unb_reserve(ctx, ln.cand, n * d * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ln.like, n * sizeof(double)));
+    UNB_TRY(h2d(ctx, ln.cand.p, params, n * d * sizeof(double), s));
+    UNB_TRY(unb_launch_loglike(ctx, kind, (const double *)ln.cand.p, (int)d, (long long)n,
+                               (double *)ln.like.p, nullptr, (const double *)ctx->lparams.p, s));
+    UNB_TRY(d2h(ctx, like, ln.like.p, n * sizeof(double), s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    return UNB_OK;
+}
+}  // namespace
+
+extern "C" int unb_loglike_gauss(unb_ctx *ctx, const double *params, size_t d, size_t n,
+                                 double *like, const double *centers, double sigma,
+                                 double norm_const)
+{
+    if (!ctx || !centers) return UNB_ERR_ARG;
+    std::vector<double> lp(d + 2);
+    memcpy(lp.data(), centers, d * sizeof(double));
+    lp[d] = sigma;
+    lp[d + 1] = norm_const;
+    return loglike_host(ctx, UNB_LOGLIKE_GAUSS, params, d, n, like, lp.data());
+}
+
+extern "C" int unb_loglike_rosenbrock(unb_ctx *ctx, const double *params, size_t d, size_t n,
+                                      double *like)
+{
+    return loglike_host(ctx, UNB_LOGLIKE_ROSENBROCK, params, d, n, like, nullptr);
+}
+
+extern "C" int unb_loglike_eggbox(unb_ctx *ctx, const double *params, size_t d, size_t n,
+                                  double *like)
+{
+    return loglike_host(ctx, UNB_LOGLIKE_EGGBOX, params, d, n, like, nullptr);
+}
+
+extern "C" int unb_loglike_gauss_dev(unb_ctx *ctx, const double *params_dev, size_t d, size_t n,
+                                     double *like_dev, const uint8_t *mask_dev,
+                                     const double *centers, double sigma, double norm_const,
+                                     void *stream)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (n == 0) return UNB_OK;
+    if (!params_dev || !like_dev || !centers) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
+    std::vector<double> lp(d + 2);
+    memcpy(lp.data(), centers, d * sizeof(double));
+    lp[d] = sigma;
+    lp[d + 1] = norm_const;
+    UNB_TRY(upload_lparams(ctx, UNB_LOGLIKE_GAUSS, lp.data(), d, s));
+    return unb_launch_loglike(ctx, UNB_LOGLIKE_GAUSS, params_dev, (int)d, (long long)n, like_dev,
+                              mask_dev, (const double *)ctx->lparams.p, s);
+}

@@ -1,0 +1,289 @@
+// unb_internal.cuh -- shared declarations of the sm_100a MLFriends engine (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ultranest_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------
+struct unb_ctx;
+int unb_fail(unb_ctx *ctx, int code, const char *fmt, ...);
+
+#define UNB_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t err__ = (call);                                                          \
+        if (err__ != cudaSuccess)                                                            \
+            return unb_fail((ctx), UNB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,             \
+                            cudaGetErrorString(err__), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define UNB_TRY(call)                                                                        \
+    do {                                                                                     \
+        int rc__ = (call);                                                                   \
+        if (rc__ != UNB_OK) return rc__;                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// growable device / pinned-host buffers
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+int unb_reserve(unb_ctx *ctx, DevBuf &b, size_t bytes);
+int unb_reserve_pinned(unb_ctx *ctx, PinBuf &b, size_t bytes);
+
+// ---------------------------------------------------------------------------------------
+// tiled live block
+//
+// The (N x d) row-major t-space live block (MLFriends.unormed) is re-laid out in HBM as
+// ceil(N / tile_n) tiles.  One tile is (dr + 1) rows of tile_n doubles, k-major:
+//     row k < dr : coordinate k of the tile's tile_n live points (0 for k >= d or i >= N)
+//     row dr     : the filter offset h_i (depends on scan mode / radius, see unb_scan.cu)
+// so a tile is ONE contiguous chunk that a single cp.async.bulk (TMA 1-D) moves into shared
+// memory, and inside shared memory the coordinates of 4 consecutive live points for a fixed k
+// are two broadcast LDS.128.  dr = d rounded up to a multiple of 4.
+// ---------------------------------------------------------------------------------------
+struct LiveTiles {
+    DevBuf tiles;     // ntiles * (dr+1) * tile_n doubles
+    DevBuf rows;      // n * d doubles, row-major copy (exact-path kernels, gathers)
+    DevBuf norms;     // n doubles: computed squared norms na_i (k-sequential FMA)
+    DevBuf namax;     // 1 double: max_i na_i (as ordered uint64)
+    size_t n = 0, d = 0, dr = 0, tile_n = 0, ntiles = 0;
+    int h_mode = -1;      // which h row is currently stored (HMODE_*)
+    double h_r2 = 0.0;
+    bool valid = false;
+};
+
+enum { HMODE_NONE = -1, HMODE_THRESH = 0, HMODE_MIN = 1 };
+
+enum ScanMode {
+    SCAN_FIND = 0,      // first index within r2 (ordered, early exit)   find_nearby
+    SCAN_COUNT = 1,     // number within r2                               count_nearby
+    SCAN_SUBTRACT = 2,  // count + ordered coordinate sum of hits         _subtract_nearby
+    SCAN_MIN = 3        // exact min distance                             compute_maxradiussq
+};
+
+enum XformKind { XF_NONE = 0, XF_SCALING = 1, XF_AFFINE = 2 };
+
+// Arguments shared by all scan kernels
+struct ScanArgs {
+    // live side
+    const double *tiles;      // tiled live block (of this launch / of round 0); NULL -> exact kernel
+    const double *live_rows;  // row-major (n x d) live block (plain exact kernel)
+    const int *live_idx;      // nullable: exact kernel scans rows live_idx[i] (bootstrap rounds)
+    const int *round_live_off;   // nullable: offset of the round's list in live_idx
+    int n_live;
+    int tile_n;
+    int d;
+    int dr;
+    // per-round addressing (bootstrap): tiles + blockIdx.y * round_tile_stride
+    long long round_tile_stride;   // in doubles; 0 for single-round launches
+    const int *round_nlive;        // nullable
+    const int *round_nitems;       // nullable
+    const int *round_item_off;     // nullable: offset of the round's item list in item_idx
+    // candidate side
+    const double *cand;       // row-major (M x d), already in the live block's space
+    const int *item_idx;      // nullable: work item -> candidate row
+    const int *out_row_idx;   // nullable: work item -> output row (default: candidate row)
+    const int *n_items_dev;   // nullable: device-resident item count (after compaction)
+    long long n_items;        // host-known item count (upper bound if n_items_dev != NULL)
+    // scan parameters
+    double r2;
+    double kappa;             // filter slack factor (see unb_scan.cu)
+    const unsigned long long *namax_bits;   // device: bits of max live squared norm (SCAN_MIN)
+    // outputs (indexed by output row)
+    long long *out_idx;       // FIND: first index / COUNT: count            (nullable for FIND)
+    unsigned char *out_mask;  // FIND: idx >= 0                               (nullable)
+    double *out_rows;         // SUBTRACT: (M x d) result rows
+    double *out_min;          // MIN: per-candidate exact min distance        (nullable)
+    unsigned long long *out_round_max;   // MIN: per-round max over candidates (ordered bits)
+    unsigned long long *stat_rechecks;   // diagnostic counter (nullable)
+};
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+struct RegionState {
+    LiveTiles live;
+    std::vector<double> snapshot;   // host copy of the mirrored unormed (row diffing)
+    int layer_kind = UNB_LAYER_IDENTITY;
+    size_t layer_d = 0;
+    DevBuf layer_shift, layer_mat;
+    std::vector<double> layer_shift_h, layer_mat_h, ell_center_h, ell_invcov_h;   // host snapshots
+    bool have_ellipsoid = false;
+    size_t ell_d = 0;
+    double enlarge = 0.0;
+    DevBuf ell_center, ell_invcov;
+    bool have_radius = false;
+    double r2 = 0.0;
+};
+
+// one in-flight chunk of a host-buffer call: its own stream, device scratch and pinned staging,
+// so chunk c+1's H2D overlaps chunk c's kernels and D2H
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr;    // H2D from pin_in finished
+    cudaEvent_t ev_done = nullptr;  // everything of the chunk finished
+    DevBuf cand, tcand, items, counter, mask, idx, like;
+    PinBuf pin_in, pin_mask, pin_like, pin_idx;
+    // deferred copy-out of a staged result
+    unsigned char *pend_mask = nullptr;
+    double *pend_like = nullptr;
+    long long *pend_idx = nullptr;
+    size_t pend_rows = 0;
+};
+
+struct unb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    long long launches = 0;
+    long long h2d_bytes = 0, d2h_bytes = 0;
+    long long last_rechecks = 0;
+    int exact_only = 0;
+    long long chunk_rows = 0;
+
+    Lane lane[2];
+    RegionState region;
+    LiveTiles scratch_live;          // stateless calls
+    DevBuf aux0, aux1, aux2, aux3, stat;
+    DevBuf lparams;                  // likelihood parameters
+    // bootstrap scratch
+    DevBuf boot_rows, boot_u, boot_tiles, boot_idx, boot_meta, boot_out, boot_ell;
+    PinBuf pin_small;
+};
+
+// ---------------------------------------------------------------------------------------
+// launchers implemented in the .cu files
+// ---------------------------------------------------------------------------------------
+int unb_live_build(unb_ctx *ctx, LiveTiles &L, const double *rows_dev, size_t n, size_t d,
+                   cudaStream_t s);
+int unb_live_update_rows(unb_ctx *ctx, LiveTiles &L, const int *rows_dev_idx, size_t nrows,
+                         cudaStream_t s);
+int unb_live_set_h(unb_ctx *ctx, LiveTiles &L, int h_mode, double r2, cudaStream_t s);
+double unb_kappa(size_t d);
+size_t unb_pick_tile_n(size_t d);
+int unb_launch_scan(unb_ctx *ctx, int mode, const ScanArgs &a, int rounds, cudaStream_t s);
+int unb_launch_gather_round_tiles(unb_ctx *ctx, const double *rows, int n, int d, int dr,
+                                  int tile_n, const int *idxA, const int *offA,
+                                  const int *nA, int rounds, long long round_tile_stride,
+                                  double *tiles, cudaStream_t s);
+
+// ellipsoid membership (+ optional candidate transform and compaction of the survivors)
+struct PrepArgs {
+    const double *pts;        // (m x d) candidates, u-space
+    long long m;
+    int d;
+    const double *center;     // ellipsoid (NULL: every row passes)
+    const double *invcov;
+    double r2;
+    unsigned char *mask;      // out: ellipsoid mask (1 byte per row); NULL to skip
+    int layer_kind;           // -1: no transform/compaction stage
+    const double *shift;
+    const double *mat;
+    double *tcand;            // out: compacted transformed rows
+    int *items;               // out: original row of each compacted row
+    int *n_items;             // in/out: device counter (must be zeroed)
+};
+int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s);
+int unb_launch_transform(unb_ctx *ctx, int kind, bool inverse, const double *in, long long m,
+                         int d, const double *shift, const double *mat, double *out,
+                         cudaStream_t s);
+int unb_launch_loglike(unb_ctx *ctx, int kind, const double *params, int d, long long n,
+                       double *like, const unsigned char *mask, const double *lparams_dev,
+                       cudaStream_t s);
+int unb_launch_enlargement_f(unb_ctx *ctx, const double *u, int d, const int *item_idx,
+                             const int *round_item_off, const int *round_nitems,
+                             int max_items, const double *ctrs, const double *invcovs,
+                             int rounds, unsigned long long *out_round_key, cudaStream_t s);
+int unb_launch_pairdist(unb_ctx *ctx, const double *pts, const long long *ids, int n, int d,
+                        double *partial_sum, long long *partial_cnt, cudaStream_t s);
+size_t unb_max_rowwise_d();
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem,
+                                             uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// order-preserving map non-negative double <-> uint64 (for atomicMax on doubles >= 0)
+__device__ __forceinline__ unsigned long long f64_bits(double x)
+{
+    return static_cast<unsigned long long>(__double_as_longlong(x));
+}
+
+// total-order key for any finite double (atomicMax on possibly negative values)
+__device__ __forceinline__ unsigned long long f64_key(double x)
+{
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+// the reference's k-sequential, non-fused squared distance (mlfriends.pyx:178-180).
+// The whole library is compiled with -fmad=false; the intrinsics make the intent explicit.
+__device__ __forceinline__ double sq_step(double acc, double a, double b)
+{
+    double diff = __dsub_rn(a, b);
+    return __dadd_rn(acc, __dmul_rn(diff, diff));
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,380 @@
+// unb_region.cu -- row-wise kernels of the MLFriends region path:
+//   * ellipsoid membership  (_inside_ellipsoid, mlfriends.pyx:882-912; einsum order of SURVEY
+//     fact 5) fused with the candidate transform and the compaction of the survivors, i.e. the
+//     first two stages of MLFriends.inside (mlfriends.pyx:1202-1206),
+//   * Scaling/Affine layer transform / untransform (mlfriends.pyx:605-620, 737-752),
+//   * vectorised likelihoods (docs/gauss.py:25-27, examples/testeggbox.py:9-11,
+//     examples/testrosenbrock.py:10-13) with NumPy's pairwise-summation order,
+//   * bootstrap enlargement factor (mlfriends.pyx:1060-1062),
+//   * mean pair distance (mlfriends.pyx:229-270).
+// One thread owns one row; the row's working vector lives in shared memory with an odd
+// double-stride so the 64-bit accesses of a warp are bank-conflict free.  The whole library is
+// built with -fmad=false: every multiply-add below is non-fused unless it says fma().
+#include "unb_internal.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr size_t ROW_SMEM_BUDGET = 200 * 1024;
+
+__host__ __device__ inline int odd_stride(int d) { return d | 1; }
+
+// threads per block so that threads * odd_stride(d) doubles fit the budget (multiple of 32)
+inline int row_threads(int d)
+{
+    size_t per = (size_t)odd_stride(d) * sizeof(double);
+    size_t t = ROW_SMEM_BUDGET / per;
+    if (t >= 128) return 128;
+    return (int)(t / 32 * 32);
+}
+
+template <typename K>
+int set_smem(unb_ctx *ctx, K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024)
+        UNB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)bytes));
+    return UNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// ellipsoid (+ transform + compaction)
+// ---------------------------------------------------------------------------------------
+__global__ void k_prep(const PrepArgs P)
+{
+    extern __shared__ __align__(16) double rowbuf[];
+    const int d = P.d, ds = odd_stride(d);
+    double *my = rowbuf + (size_t)threadIdx.x * ds;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = j < P.m;
+    bool inside = valid;
+    if (P.center) {
+        double acc = 0.0;
+        if (valid) {
+            const double *p = P.pts + j * d;
+            for (int k = 0; k < d; k++) my[k] = __dsub_rn(p[k], __ldg(P.center + k));
+            // np.einsum('ij,jk,ik->i'): acc += (d_j * A_jk) * d_k, j outer, k inner
+            for (int jj = 0; jj < d; jj++) {
+                const double dj = my[jj];
+                const double *Arow = P.invcov + (size_t)jj * d;
+                for (int k = 0; k < d; k++)
+                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
+            }
+        }
+        inside = valid && (acc <= P.r2);
+        if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
+    }
+    if (P.layer_kind < 0) return;
+
+    // compaction of the survivors (warp-aggregated; order is irrelevant because every result
+    // is scattered back through items[])
+    const unsigned ball = __ballot_sync(FULL, inside);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && ball) base = atomicAdd(P.n_items, __popc(ball));
+    base = __shfl_sync(FULL, base, 0);
+    if (!inside) return;
+    const int pos = base + __popc(ball & ((1u << (threadIdx.x & 31)) - 1));
+    P.items[pos] = (int)j;
+    const double *p = P.pts + j * d;
+    double *out = P.tcand + (size_t)pos * d;
+    if (P.layer_kind == UNB_LAYER_AFFINE) {
+        // DEFINED order: x = w - ctr, t_j = fma-chain over k ascending
+        for (int k = 0; k < d; k++) my[k] = __dsub_rn(p[k], __ldg(P.shift + k));
+        for (int jj = 0; jj < d; jj++) {
+            double t = 0.0;
+            for (int k = 0; k < d; k++) t = fma(my[k], __ldg(P.mat + (size_t)k * d + jj), t);
+            out[jj] = t;
+        }
+    } else if (P.layer_kind == UNB_LAYER_SCALING) {
+        for (int k = 0; k < d; k++)
+            out[k] = __ddiv_rn(__dsub_rn(p[k], __ldg(P.shift + k)), __ldg(P.mat + k));
+    } else {
+        for (int k = 0; k < d; k++) out[k] = p[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// layer transforms
+// ---------------------------------------------------------------------------------------
+__global__ void k_transform(int kind, int inverse, const double *__restrict__ in, long long m,
+                            int d, const double *__restrict__ shift,
+                            const double *__restrict__ mat, double *__restrict__ out)
+{
+    extern __shared__ __align__(16) double rowbuf[];
+    const int ds = odd_stride(d);
+    double *my = rowbuf + (size_t)threadIdx.x * ds;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const double *p = in + j * d;
+    double *o = out + j * d;
+    if (kind == UNB_LAYER_AFFINE) {
+        if (!inverse) {
+            for (int k = 0; k < d; k++) my[k] = __dsub_rn(p[k], __ldg(shift + k));
+            for (int jj = 0; jj < d; jj++) {
+                double t = 0.0;
+                for (int k = 0; k < d; k++) t = fma(my[k], __ldg(mat + (size_t)k * d + jj), t);
+                o[jj] = t;
+            }
+        } else {
+            for (int k = 0; k < d; k++) my[k] = p[k];
+            for (int jj = 0; jj < d; jj++) {
+                double t = 0.0;
+                for (int k = 0; k < d; k++) t = fma(my[k], __ldg(mat + (size_t)k * d + jj), t);
+                o[jj] = __dadd_rn(t, __ldg(shift + jj));
+            }
+        }
+    } else if (kind == UNB_LAYER_SCALING) {
+        if (!inverse)
+            for (int k = 0; k < d; k++)
+                o[k] = __ddiv_rn(__dsub_rn(p[k], __ldg(shift + k)), __ldg(mat + k));
+        else
+            for (int k = 0; k < d; k++)
+                o[k] = __dadd_rn(__dmul_rn(p[k], __ldg(mat + k)), __ldg(shift + k));
+    } else {
+        for (int k = 0; k < d; k++) o[k] = p[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// NumPy pairwise summation (numpy/_core/src/umath/loops_utils.h.src, PW_BLOCKSIZE = 128)
+// ---------------------------------------------------------------------------------------
+__device__ double pw_block(const double *a, int n)
+{
+    if (n < 8) {
+        double res = 0.;
+        for (int i = 0; i < n; i++) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+        r0 = __dadd_rn(r0, a[i + 0]); r1 = __dadd_rn(r1, a[i + 1]);
+        r2 = __dadd_rn(r2, a[i + 2]); r3 = __dadd_rn(r3, a[i + 3]);
+        r4 = __dadd_rn(r4, a[i + 4]); r5 = __dadd_rn(r5, a[i + 5]);
+        r6 = __dadd_rn(r6, a[i + 6]); r7 = __dadd_rn(r7, a[i + 7]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (; i < n; i++) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__device__ double np_pairwise_sum(const double *a, int n)
+{
+    if (n <= 128) return pw_block(a, n);
+    // explicit post-order walk of the halving tree (n2 = n/2 rounded down to a multiple of 8)
+    int off[20], len[20], phase[20];
+    double left[20];
+    int sp = 0;
+    off[0] = 0; len[0] = n; phase[0] = 0; left[0] = 0.0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        if (len[sp] <= 128) {
+            ret = pw_block(a + off[sp], len[sp]);
+            sp--;
+            continue;
+        }
+        int n2 = len[sp] / 2;
+        n2 -= n2 % 8;
+        if (phase[sp] == 0) {
+            phase[sp] = 1;
+            off[sp + 1] = off[sp]; len[sp + 1] = n2; phase[sp + 1] = 0;
+            sp++;
+        } else if (phase[sp] == 1) {
+            left[sp] = ret;
+            phase[sp] = 2;
+            off[sp + 1] = off[sp] + n2; len[sp + 1] = len[sp] - n2; phase[sp + 1] = 0;
+            sp++;
+        } else {
+            ret = __dadd_rn(left[sp], ret);
+            sp--;
+        }
+    }
+    return ret;
+}
+
+// ---------------------------------------------------------------------------------------
+// vectorised likelihoods.  lp = device parameter block:
+//   GAUSS: centers[d], sigma, norm_const
+// mask (nullable): rows with mask == 0 get -inf (integrator.py:1797-1802 only evaluates accepted
+// rows and leaves the rest at -inf).
+// ---------------------------------------------------------------------------------------
+__global__ void k_loglike(int kind, const double *__restrict__ params, int d, long long n,
+                          double *__restrict__ like, const unsigned char *__restrict__ mask,
+                          const double *__restrict__ lp)
+{
+    extern __shared__ __align__(16) double rowbuf[];
+    const int ds = odd_stride(d);
+    double *t = rowbuf + (size_t)threadIdx.x * ds;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (mask && !mask[j]) {
+        like[j] = -__longlong_as_double(0x7ff0000000000000LL);
+        return;
+    }
+    const double *p = params + j * d;
+    if (kind == UNB_LOGLIKE_GAUSS) {
+        const double sigma = __ldg(lp + d), norm_const = __ldg(lp + d + 1);
+        for (int i = 0; i < d; i++) {
+            double z = __ddiv_rn(__dsub_rn(p[i], __ldg(lp + i)), sigma);
+            t[i] = __dmul_rn(z, z);
+        }
+        like[j] = __dsub_rn(__dmul_rn(-0.5, np_pairwise_sum(t, d)), norm_const);
+    } else if (kind == UNB_LOGLIKE_ROSENBROCK) {
+        for (int i = 0; i + 1 < d; i++) {
+            const double a = p[i], b = p[i + 1];
+            const double u = __dsub_rn(b, __dmul_rn(a, a));
+            const double v = __dsub_rn(1.0, a);
+            t[i] = __dadd_rn(__dmul_rn(100.0, __dmul_rn(u, u)), __dmul_rn(v, v));
+        }
+        like[j] = __dmul_rn(-2.0, np_pairwise_sum(t, d - 1));
+    } else {   // eggbox
+        double chi = 1.0;
+        for (int i = 0; i < d; i++) chi = __dmul_rn(chi, cos(__ddiv_rn(p[i], 2.0)));
+        like[j] = pow(__dadd_rn(2.0, chi), 5.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// bootstrap enlargement: per round, max over the left-out rows of the einsum form
+// ---------------------------------------------------------------------------------------
+__global__ void k_enlargement_f(const double *__restrict__ u, int d,
+                                const int *__restrict__ item_idx,
+                                const int *__restrict__ round_item_off,
+                                const int *__restrict__ round_nitems,
+                                const double *__restrict__ ctrs,
+                                const double *__restrict__ invcovs,
+                                unsigned long long *__restrict__ out_round_key)
+{
+    extern __shared__ __align__(16) double rowbuf[];
+    const int ds = odd_stride(d);
+    double *my = rowbuf + (size_t)threadIdx.x * ds;
+    const int round = blockIdx.y;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = item < round_nitems[round];
+    unsigned long long key = 0;   // below every finite double's key
+    if (valid) {
+        const int row = item_idx[round_item_off[round] + item];
+        const double *p = u + (size_t)row * d;
+        const double *ctr = ctrs + (size_t)round * d;
+        const double *A = invcovs + (size_t)round * d * d;
+        for (int k = 0; k < d; k++) my[k] = __dsub_rn(p[k], __ldg(ctr + k));
+        double acc = 0.0;
+        for (int jj = 0; jj < d; jj++) {
+            const double dj = my[jj];
+            for (int k = 0; k < d; k++)
+                acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(A + (size_t)jj * d + k)), my[k]));
+        }
+        key = f64_key(acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(FULL, key, o);
+        key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(out_round_key + round, key);
+}
+
+// ---------------------------------------------------------------------------------------
+// mean pair distance: thread j accumulates sqrt(D_ij) over i < j in the same cluster
+// ---------------------------------------------------------------------------------------
+__global__ void k_pairdist(const double *__restrict__ pts, const long long *__restrict__ ids,
+                           int n, int d, double *__restrict__ partial_sum,
+                           long long *__restrict__ partial_cnt)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double total = 0.0;
+    long long cnt = 0;
+    const long long cj = ids[j];
+    if (cj != 0) {
+        const double *b = pts + (size_t)j * d;
+        for (int i = 0; i < j; i++) {
+            if (ids[i] != cj) continue;
+            const double *a = pts + (size_t)i * d;
+            double D = 0.0;
+            for (int k = 0; k < d; k++) D = sq_step(D, a[k], b[k]);
+            total = __dadd_rn(total, sqrt(D));
+            cnt++;
+        }
+    }
+    partial_sum[j] = total;
+    partial_cnt[j] = cnt;
+}
+
+}  // namespace
+
+size_t unb_max_rowwise_d() { return ROW_SMEM_BUDGET / sizeof(double) / 32 - 1; }
+
+int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s)
+{
+    if (p.m <= 0) return UNB_OK;
+    const int threads = row_threads(p.d);
+    if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%d too large for the row kernels", p.d);
+    const size_t smem = (size_t)threads * odd_stride(p.d) * sizeof(double);
+    UNB_TRY(set_smem(ctx, k_prep, smem));
+    k_prep<<<(unsigned)((p.m + threads - 1) / threads), threads, smem, s>>>(p);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+int unb_launch_transform(unb_ctx *ctx, int kind, bool inverse, const double *in, long long m,
+                         int d, const double *shift, const double *mat, double *out,
+                         cudaStream_t s)
+{
+    if (m <= 0) return UNB_OK;
+    const int threads = row_threads(d);
+    if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%d too large for the row kernels", d);
+    const size_t smem = (size_t)threads * odd_stride(d) * sizeof(double);
+    UNB_TRY(set_smem(ctx, k_transform, smem));
+    k_transform<<<(unsigned)((m + threads - 1) / threads), threads, smem, s>>>(
+        kind, inverse ? 1 : 0, in, m, d, shift, mat, out);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+int unb_launch_loglike(unb_ctx *ctx, int kind, const double *params, int d, long long n,
+                       double *like, const unsigned char *mask, const double *lparams_dev,
+                       cudaStream_t s)
+{
+    if (n <= 0) return UNB_OK;
+    const int threads = row_threads(d);
+    if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%d too large for the row kernels", d);
+    const size_t smem = (size_t)threads * odd_stride(d) * sizeof(double);
+    UNB_TRY(set_smem(ctx, k_loglike, smem));
+    k_loglike<<<(unsigned)((n + threads - 1) / threads), threads, smem, s>>>(
+        kind, params, d, n, like, mask, lparams_dev);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+int unb_launch_enlargement_f(unb_ctx *ctx, const double *u, int d, const int *item_idx,
+                             const int *round_item_off, const int *round_nitems,
+                             int max_items, const double *ctrs, const double *invcovs,
+                             int rounds, unsigned long long *out_round_key, cudaStream_t s)
+{
+    if (rounds <= 0 || max_items <= 0) return UNB_OK;
+    int threads = row_threads(d);
+    if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%d too large for the row kernels", d);
+    if (threads > 64) threads = 64;   // more blocks: the rounds are small
+    const size_t smem = (size_t)threads * odd_stride(d) * sizeof(double);
+    UNB_TRY(set_smem(ctx, k_enlargement_f, smem));
+    dim3 grid((unsigned)((max_items + threads - 1) / threads), (unsigned)rounds);
+    k_enlargement_f<<<grid, threads, smem, s>>>(u, d, item_idx, round_item_off, round_nitems,
+                                               ctrs, invcovs, out_round_key);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+int unb_launch_pairdist(unb_ctx *ctx, const double *pts, const long long *ids, int n, int d,
+                        double *partial_sum, long long *partial_cnt, cudaStream_t s)
+{
+    if (n <= 0) return UNB_OK;
+    k_pairdist<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(pts, ids, n, d, partial_sum, partial_cnt);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}

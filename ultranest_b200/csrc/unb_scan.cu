@@ -1,0 +1,803 @@
+// unb_scan.cu -- candidate-vs-live-point pair scans (find_nearby, count_nearby,
+// _subtract_nearby, compute_maxradiussq of ultranest/mlfriends.pyx) as sm_100a kernels.
+//
+// Arithmetic contract: the reference decides every pair with the
+// k-sequential, non-fused fp64 distance  D = (((0 + (a0-b0)^2) + (a1-b1)^2) + ...)  and `<=`.
+// Evaluating D costs 3 DP instructions per pair-dimension.  The kernels here get the SAME
+// decisions with ~1 DFMA per pair-dimension:
+//
+//   filter : acc = h_i + sum_k a_ik * b_jk  (one DFMA per k, h_i rides in as the first addend)
+//            with the identity  a.b + (r2 - |a|^2)/2 - |b|^2/2 = (r2 - D_true)/2.
+//            A pair can only satisfy D <= r2 if acc >= thr_j, once h_i / thr_j are widened by
+//            kappa * (|a|^2 + |b|^2 + r2), kappa = (8d+64) * 2^-53, which dominates every
+//            rounding error of the filter AND of the reference's own sum (bound derived in
+//            DESIGN.md "Filter bound").  The comparison uses only the high word of acc
+//            (integer ISETP, off the DP pipe) with one more unit of slack.
+//   decide : pairs that pass the filter (a few per candidate) are re-evaluated with the
+//            reference's exact sequence (sq_step) and compared with `<=` -- so outputs are
+//            bit-identical to the Cython, independent of the filter.
+//
+// The live block is streamed through shared memory tile by tile with TMA 1-D bulk copies
+// (cp.async.bulk + mbarrier, double buffered); candidates live in registers (d <= 32) or in
+// shared memory (d > 32).  No tensor cores: this is an fp64 CUDA-core scan.
+#include "unb_internal.cuh"
+
+#include <climits>
+
+namespace {
+
+constexpr int SCAN_THREADS = 128;
+constexpr int TN = 4;               // live points per register-tile column group
+constexpr int REG_TILE_N = 64;      // live points per shared-memory tile (register kernel)
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// ---------------------------------------------------------------------------------------
+// live-block layout kernels
+// ---------------------------------------------------------------------------------------
+
+// one thread per tile slot: writes the coordinate rows and the squared norm
+__global__ void k_live_build(const double *__restrict__ rows, int n, int d, int dr, int tile_n,
+                             int ntiles, double *__restrict__ tiles, double *__restrict__ norms)
+{
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= ntiles * tile_n) return;
+    int t = slot / tile_n, c = slot - t * tile_n;
+    double *T = tiles + (size_t)t * (dr + 1) * tile_n + c;
+    double na = 0.0;
+    for (int k = 0; k < dr; k++) {
+        double v = (slot < n && k < d) ? rows[(size_t)slot * d + k] : 0.0;
+        T[(size_t)k * tile_n] = v;
+        na = fma(v, v, na);
+    }
+    norms[slot] = (slot < n) ? na : 0.0;
+}
+
+// rewrite selected rows after an in-place mutation of the mirrored block
+__global__ void k_live_update_rows(const double *__restrict__ rows, const int *__restrict__ idx,
+                                   int nrows, int d, int dr, int tile_n,
+                                   double *__restrict__ tiles, double *__restrict__ norms)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    int slot = idx[r];
+    int t = slot / tile_n, c = slot - t * tile_n;
+    double *T = tiles + (size_t)t * (dr + 1) * tile_n + c;
+    double na = 0.0;
+    for (int k = 0; k < dr; k++) {
+        double v = (k < d) ? rows[(size_t)slot * d + k] : 0.0;
+        T[(size_t)k * tile_n] = v;
+        na = fma(v, v, na);
+    }
+    norms[slot] = na;
+}
+
+__global__ void k_norm_max(const double *__restrict__ norms, int n, unsigned long long *out)
+{
+    double m = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        m = fmax(m, norms[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, f64_bits(m));
+}
+
+// h row of every tile.  THRESH: h_i = ((1+kappa) r2 - (1-kappa) |a_i|^2) / 2,  MIN: -|a_i|^2/2,
+// padding slots get -1e300 so they can never pass a filter.
+__global__ void k_live_set_h(const double *__restrict__ norms, int n, int dr, int tile_n,
+                             int ntiles, int h_mode, double r2, double kappa,
+                             double *__restrict__ tiles)
+{
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= ntiles * tile_n) return;
+    int t = slot / tile_n, c = slot - t * tile_n;
+    double h = -1e300;
+    if (slot < n) {
+        double na = norms[slot];
+        if (h_mode == HMODE_THRESH) {
+            double r2w = __dmul_rn(r2, __dadd_rn(1.0, kappa));
+            double naw = __dmul_rn(na, __dsub_rn(1.0, kappa));
+            h = __dmul_rn(0.5, __dsub_rn(r2w, naw));
+        } else {
+            h = __dmul_rn(-0.5, na);
+        }
+    }
+    tiles[(size_t)t * (dr + 1) * tile_n + (size_t)dr * tile_n + c] = h;
+}
+
+// bootstrap: per-round compacted tiles (selected rows only, original order) with MIN-mode h
+__global__ void k_gather_round_tiles(const double *__restrict__ rows, int d, int dr, int tile_n,
+                                     const int *__restrict__ idxA, const int *__restrict__ offA,
+                                     const int *__restrict__ nA, long long round_tile_stride,
+                                     double *__restrict__ tiles)
+{
+    int round = blockIdx.y;
+    int na = nA[round];
+    int ntiles = (na + tile_n - 1) / tile_n;
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= ntiles * tile_n) return;
+    int t = slot / tile_n, c = slot - t * tile_n;
+    double *T = tiles + (size_t)round * round_tile_stride + (size_t)t * (dr + 1) * tile_n + c;
+    int src = (slot < na) ? idxA[offA[round] + slot] : -1;
+    double nrm = 0.0;
+    for (int k = 0; k < dr; k++) {
+        double v = (src >= 0 && k < d) ? rows[(size_t)src * d + k] : 0.0;
+        T[(size_t)k * tile_n] = v;
+        nrm = fma(v, v, nrm);
+    }
+    T[(size_t)dr * tile_n] = (src >= 0) ? __dmul_rn(-0.5, nrm) : -1e300;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-candidate scan state
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+struct CState {
+    int valid;
+    int first;      // FIND
+    int thrkey;     // FIND / COUNT / SUBTRACT: high word of the filter threshold, minus 1
+    int cnt;        // COUNT / SUBTRACT
+    double best;    // MIN: exact minimum so far
+    double amax;    // MIN: largest filter value seen
+    double thr;     // MIN: amax - slack
+    double slack;   // MIN
+};
+
+template <int MODE>
+__device__ __forceinline__ void cs_init(CState<MODE> &s, bool valid, double nb,
+                                        const ScanArgs &A)
+{
+    s.valid = valid;
+    s.first = -1;
+    s.cnt = 0;
+    s.best = 1e300;
+    s.amax = -1e300;
+    if (MODE == SCAN_MIN) {
+        double namax = __longlong_as_double((long long)*A.namax_bits);
+        s.slack = __dmul_rn(A.kappa, __dadd_rn(namax, nb));
+        s.thr = valid ? -pos_inf() : pos_inf();
+        s.thrkey = 0;
+    } else {
+        double thr = __dmul_rn(0.5, __dmul_rn(nb, __dsub_rn(1.0, A.kappa)));
+        s.thrkey = valid ? (__double2hiint(thr) - 1) : INT_MAX;
+        s.thr = 0.0;
+        s.slack = 0.0;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ bool cs_flag(const CState<MODE> &s, double acc)
+{
+    if (MODE == SCAN_MIN) return acc >= s.thr;
+    return __double2hiint(acc) >= s.thrkey;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool cs_done(const CState<MODE> &s)
+{
+    if (MODE == SCAN_FIND) return (!s.valid) || s.first >= 0;
+    return !s.valid;
+}
+
+// ---------------------------------------------------------------------------------------
+// register kernel: d <= 32 (DR = d rounded up to 4), TM candidates per thread
+// ---------------------------------------------------------------------------------------
+// The tile is read through a volatile pointer here on purpose: otherwise the compiler merges
+// these loads with the filter loop's and keeps the whole tile column block alive (spilled)
+// across the rarely taken branch.
+template <int DR>
+__device__ __forceinline__ double exact_dist_reg(const double (&a)[DR], const double *Tcol)
+{
+    const volatile double *Tv = Tcol;
+    double D = 0.0;
+#pragma unroll
+    for (int k = 0; k < DR; k++) D = sq_step(D, Tv[k * REG_TILE_N], a[k]);
+    return D;
+}
+
+// resident blocks per SM the register budget is planned for: candidates (2*TM*DR registers)
+// + accumulators (2*TM*TN) + addressing/state
+constexpr int reg_min_blocks(int DR, int TM)
+{
+    const int need = 2 * TM * DR + 2 * TM * TN + 48;
+    return need <= 128 ? 4 : (need <= 168 ? 3 : 2);
+}
+
+template <int DR, int TM, int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS, reg_min_blocks(DR, TM)) k_scan_reg(const ScanArgs A)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    constexpr int TILE_DOUBLES = (DR + 1) * REG_TILE_N;
+    constexpr uint32_t TILE_BYTES = TILE_DOUBLES * sizeof(double);
+    double *tbuf = reinterpret_cast<double *>(smem_raw + 128);
+
+    const int tid = threadIdx.x;
+    const int round = blockIdx.y;
+    const double *tiles = A.tiles + (long long)round * A.round_tile_stride;
+    const int n_live = A.round_nlive ? A.round_nlive[round] : A.n_live;
+    const int ntiles = (n_live + REG_TILE_N - 1) / REG_TILE_N;
+    const long long n_items =
+        A.round_nitems ? (long long)A.round_nitems[round]
+                       : (A.n_items_dev ? (long long)*A.n_items_dev : A.n_items);
+    const int *items = A.item_idx ? A.item_idx + (A.round_item_off ? A.round_item_off[round] : 0)
+                                  : nullptr;
+    const long long base = (long long)blockIdx.x * (SCAN_THREADS * TM);
+    if (base >= n_items) return;
+    const int d = A.d;
+
+    // ---- candidates into registers
+    double a[TM][DR];
+    long long row[TM], orow[TM];
+    CState<MODE> st[TM];
+#pragma unroll
+    for (int m = 0; m < TM; m++) {
+        long long item = base + (long long)m * SCAN_THREADS + tid;
+        bool valid = item < n_items;
+        row[m] = valid ? (items ? (long long)items[item] : item) : -1;
+        orow[m] = valid ? (A.out_row_idx ? (long long)A.out_row_idx[item] : row[m]) : -1;
+        double nb = 0.0;
+#pragma unroll
+        for (int k = 0; k < DR; k++) {
+            double v = (valid && k < d) ? A.cand[row[m] * d + k] : 0.0;
+            a[m][k] = v;
+            nb = fma(v, v, nb);
+        }
+        cs_init<MODE>(st[m], valid, nb, A);
+        if (MODE == SCAN_SUBTRACT && valid)
+            for (int k = 0; k < d; k++) A.out_rows[orow[m] * d + k] = 0.0;
+    }
+
+    // ---- TMA pipeline over live tiles
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0 && ntiles > 0) {
+        mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
+        tma_bulk_g2s(tbuf, tiles, TILE_BYTES, &bars[0]);
+        if (ntiles > 1) {
+            mbar_arrive_expect_tx(&bars[1], TILE_BYTES);
+            tma_bulk_g2s(tbuf + TILE_DOUBLES, tiles + TILE_DOUBLES, TILE_BYTES, &bars[1]);
+        }
+    }
+
+    bool warp_done = false;
+    unsigned long long rechecks = 0;
+    int inflight = -1;   // tile index still in flight when the loop is left early
+    for (int t = 0; t < ntiles; t++) {
+        const int buf = t & 1;
+        mbar_wait(&bars[buf], (t >> 1) & 1);
+        const double *T = tbuf + buf * TILE_DOUBLES;
+        if (!warp_done) {
+#pragma unroll 1
+            for (int g = 0; g < REG_TILE_N / TN; g++) {
+                const double *Tg = T + g * TN;
+                double acc[TM][TN];
+                {
+                    const double4 h = *reinterpret_cast<const double4 *>(Tg + DR * REG_TILE_N);
+#pragma unroll
+                    for (int m = 0; m < TM; m++) {
+                        acc[m][0] = h.x; acc[m][1] = h.y; acc[m][2] = h.z; acc[m][3] = h.w;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < DR; k++) {
+                    const double4 b = *reinterpret_cast<const double4 *>(Tg + k * REG_TILE_N);
+#pragma unroll
+                    for (int m = 0; m < TM; m++) {
+                        acc[m][0] = fma(a[m][k], b.x, acc[m][0]);
+                        acc[m][1] = fma(a[m][k], b.y, acc[m][1]);
+                        acc[m][2] = fma(a[m][k], b.z, acc[m][2]);
+                        acc[m][3] = fma(a[m][k], b.w, acc[m][3]);
+                    }
+                }
+                bool any = false;
+#pragma unroll
+                for (int m = 0; m < TM; m++)
+#pragma unroll
+                    for (int n = 0; n < TN; n++) any |= cs_flag<MODE>(st[m], acc[m][n]);
+                if (any) {
+                    // ---- decide: exact reference arithmetic for the pairs that passed the filter
+                    const int gbase = t * REG_TILE_N + g * TN;
+#pragma unroll
+                    for (int m = 0; m < TM; m++) {
+#pragma unroll
+                        for (int n = 0; n < TN; n++) {
+                            if (cs_flag<MODE>(st[m], acc[m][n])) {
+                                rechecks++;
+                                const double D = exact_dist_reg<DR>(a[m], Tg + n);
+                                if (MODE == SCAN_MIN) {
+                                    st[m].best = fmin(st[m].best, D);
+                                    st[m].amax = fmax(st[m].amax, acc[m][n]);
+                                    st[m].thr = __dsub_rn(st[m].amax, st[m].slack);
+                                } else if (D <= A.r2) {
+                                    if (MODE == SCAN_FIND) {
+                                        st[m].first = gbase + n;
+                                        st[m].thrkey = INT_MAX;   // later indices cannot win
+                                    } else {
+                                        st[m].cnt++;
+                                        if (MODE == SCAN_SUBTRACT) {
+                                            const volatile double *Tv = Tg + n;
+                                            for (int k = 0; k < d; k++)
+                                                A.out_rows[orow[m] * d + k] += Tv[k * REG_TILE_N];
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            bool done = true;
+#pragma unroll
+            for (int m = 0; m < TM; m++) done &= cs_done<MODE>(st[m]);
+            warp_done = __all_sync(FULL, done);
+        }
+        const bool all_done = __syncthreads_and(warp_done);
+        if (all_done) {
+            if (t + 1 < ntiles) inflight = t + 1;
+            break;
+        }
+        if (tid == 0 && t + 2 < ntiles) {
+            mbar_arrive_expect_tx(&bars[buf], TILE_BYTES);
+            tma_bulk_g2s(tbuf + buf * TILE_DOUBLES, tiles + (size_t)(t + 2) * TILE_DOUBLES,
+                         TILE_BYTES, &bars[buf]);
+        }
+    }
+    if (inflight >= 0) mbar_wait(&bars[inflight & 1], (inflight >> 1) & 1);
+
+    // ---- results
+    double blockmax = 0.0;
+#pragma unroll
+    for (int m = 0; m < TM; m++) {
+        if (!st[m].valid) continue;
+        if (MODE == SCAN_FIND) {
+            if (A.out_idx) A.out_idx[orow[m]] = st[m].first;
+            if (A.out_mask) A.out_mask[orow[m]] = st[m].first >= 0;
+        } else if (MODE == SCAN_COUNT) {
+            A.out_idx[orow[m]] = st[m].cnt;
+        } else if (MODE == SCAN_SUBTRACT) {
+            const double cnt = (double)st[m].cnt;
+            for (int k = 0; k < d; k++) {
+                double s = A.out_rows[orow[m] * d + k];
+                A.out_rows[orow[m] * d + k] = __dsub_rn(A.cand[row[m] * d + k], __ddiv_rn(s, cnt));
+            }
+        } else {
+            if (A.out_min) A.out_min[orow[m]] = st[m].best;
+            blockmax = fmax(blockmax, st[m].best);
+        }
+    }
+    if (MODE == SCAN_MIN) {
+        for (int o = 16; o > 0; o >>= 1) blockmax = fmax(blockmax, __shfl_xor_sync(FULL, blockmax, o));
+        if ((tid & 31) == 0 && A.out_round_max)
+            atomicMax(A.out_round_max + round, f64_bits(blockmax));
+    }
+    if (A.stat_rechecks) {
+        for (int o = 16; o > 0; o >>= 1) rechecks += __shfl_xor_sync(FULL, rechecks, o);
+        if ((tid & 31) == 0 && rechecks) atomicAdd(A.stat_rechecks, rechecks);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic kernel: any d that fits shared memory; candidates k-major in shared memory,
+// one candidate per thread, 8 live points per register group
+// ---------------------------------------------------------------------------------------
+constexpr int GTN = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_gen(const ScanArgs A)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    const int dr = A.dr, d = A.d, tile_n = A.tile_n;
+    const int tile_doubles = (dr + 1) * tile_n;
+    const uint32_t tile_bytes = (uint32_t)tile_doubles * sizeof(double);
+    double *cs = reinterpret_cast<double *>(smem_raw + 128);       // [dr][SCAN_THREADS]
+    double *tbuf = cs + (size_t)dr * SCAN_THREADS;
+
+    const int tid = threadIdx.x;
+    const int round = blockIdx.y;
+    const double *tiles = A.tiles + (long long)round * A.round_tile_stride;
+    const int n_live = A.round_nlive ? A.round_nlive[round] : A.n_live;
+    const int ntiles = (n_live + tile_n - 1) / tile_n;
+    const long long n_items =
+        A.round_nitems ? (long long)A.round_nitems[round]
+                       : (A.n_items_dev ? (long long)*A.n_items_dev : A.n_items);
+    const int *items = A.item_idx ? A.item_idx + (A.round_item_off ? A.round_item_off[round] : 0)
+                                  : nullptr;
+    const long long base = (long long)blockIdx.x * SCAN_THREADS;
+    if (base >= n_items) return;
+
+    const long long item = base + tid;
+    const bool valid = item < n_items;
+    const long long row = valid ? (items ? (long long)items[item] : item) : -1;
+    const long long orow = valid ? (A.out_row_idx ? (long long)A.out_row_idx[item] : row) : -1;
+    double nb = 0.0;
+    for (int k = 0; k < dr; k++) {
+        double v = (valid && k < d) ? A.cand[row * d + k] : 0.0;
+        cs[(size_t)k * SCAN_THREADS + tid] = v;
+        nb = fma(v, v, nb);
+    }
+    CState<MODE> st;
+    cs_init<MODE>(st, valid, nb, A);
+    if (MODE == SCAN_SUBTRACT && valid)
+        for (int k = 0; k < d; k++) A.out_rows[orow * d + k] = 0.0;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0 && ntiles > 0) {
+        mbar_arrive_expect_tx(&bars[0], tile_bytes);
+        tma_bulk_g2s(tbuf, tiles, tile_bytes, &bars[0]);
+        if (ntiles > 1) {
+            mbar_arrive_expect_tx(&bars[1], tile_bytes);
+            tma_bulk_g2s(tbuf + tile_doubles, tiles + tile_doubles, tile_bytes, &bars[1]);
+        }
+    }
+
+    bool warp_done = false;
+    unsigned long long rechecks = 0;
+    int inflight = -1;
+    const double *mycs = cs + tid;
+    for (int t = 0; t < ntiles; t++) {
+        const int buf = t & 1;
+        mbar_wait(&bars[buf], (t >> 1) & 1);
+        const double *T = tbuf + (size_t)buf * tile_doubles;
+        if (!warp_done) {
+            for (int g = 0; g < tile_n / GTN; g++) {
+                const double *Tg = T + g * GTN;
+                double acc[GTN];
+                {
+                    const double4 h0 = *reinterpret_cast<const double4 *>(Tg + (size_t)dr * tile_n);
+                    const double4 h1 = *reinterpret_cast<const double4 *>(Tg + (size_t)dr * tile_n + 4);
+                    acc[0] = h0.x; acc[1] = h0.y; acc[2] = h0.z; acc[3] = h0.w;
+                    acc[4] = h1.x; acc[5] = h1.y; acc[6] = h1.z; acc[7] = h1.w;
+                }
+#pragma unroll 4
+                for (int k = 0; k < dr; k++) {
+                    const double av = mycs[(size_t)k * SCAN_THREADS];
+                    const double4 b0 = *reinterpret_cast<const double4 *>(Tg + (size_t)k * tile_n);
+                    const double4 b1 = *reinterpret_cast<const double4 *>(Tg + (size_t)k * tile_n + 4);
+                    acc[0] = fma(av, b0.x, acc[0]); acc[1] = fma(av, b0.y, acc[1]);
+                    acc[2] = fma(av, b0.z, acc[2]); acc[3] = fma(av, b0.w, acc[3]);
+                    acc[4] = fma(av, b1.x, acc[4]); acc[5] = fma(av, b1.y, acc[5]);
+                    acc[6] = fma(av, b1.z, acc[6]); acc[7] = fma(av, b1.w, acc[7]);
+                }
+                bool any = false;
+#pragma unroll
+                for (int n = 0; n < GTN; n++) any |= cs_flag<MODE>(st, acc[n]);
+                if (any) {
+                    const int gbase = t * tile_n + g * GTN;
+#pragma unroll
+                    for (int n = 0; n < GTN; n++) {
+                        if (cs_flag<MODE>(st, acc[n])) {
+                            rechecks++;
+                            double D = 0.0;
+                            const volatile double *Tv = Tg + n;
+                            for (int k = 0; k < d; k++)
+                                D = sq_step(D, Tv[(size_t)k * tile_n], mycs[(size_t)k * SCAN_THREADS]);
+                            if (MODE == SCAN_MIN) {
+                                st.best = fmin(st.best, D);
+                                st.amax = fmax(st.amax, acc[n]);
+                                st.thr = __dsub_rn(st.amax, st.slack);
+                            } else if (D <= A.r2) {
+                                if (MODE == SCAN_FIND) {
+                                    st.first = gbase + n;
+                                    st.thrkey = INT_MAX;
+                                } else {
+                                    st.cnt++;
+                                    if (MODE == SCAN_SUBTRACT)
+                                        for (int k = 0; k < d; k++)
+                                            A.out_rows[orow * d + k] += Tv[(size_t)k * tile_n];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            warp_done = __all_sync(FULL, cs_done<MODE>(st));
+        }
+        const bool all_done = __syncthreads_and(warp_done);
+        if (all_done) {
+            if (t + 1 < ntiles) inflight = t + 1;
+            break;
+        }
+        if (tid == 0 && t + 2 < ntiles) {
+            mbar_arrive_expect_tx(&bars[buf], tile_bytes);
+            tma_bulk_g2s(tbuf + (size_t)buf * tile_doubles, tiles + (size_t)(t + 2) * tile_doubles,
+                         tile_bytes, &bars[buf]);
+        }
+    }
+    if (inflight >= 0) mbar_wait(&bars[inflight & 1], (inflight >> 1) & 1);
+
+    double blockmax = 0.0;
+    if (valid) {
+        if (MODE == SCAN_FIND) {
+            if (A.out_idx) A.out_idx[orow] = st.first;
+            if (A.out_mask) A.out_mask[orow] = st.first >= 0;
+        } else if (MODE == SCAN_COUNT) {
+            A.out_idx[orow] = st.cnt;
+        } else if (MODE == SCAN_SUBTRACT) {
+            const double cnt = (double)st.cnt;
+            for (int k = 0; k < d; k++) {
+                double s = A.out_rows[orow * d + k];
+                A.out_rows[orow * d + k] = __dsub_rn(A.cand[row * d + k], __ddiv_rn(s, cnt));
+            }
+        } else {
+            if (A.out_min) A.out_min[orow] = st.best;
+            blockmax = st.best;
+        }
+    }
+    if (MODE == SCAN_MIN) {
+        for (int o = 16; o > 0; o >>= 1) blockmax = fmax(blockmax, __shfl_xor_sync(FULL, blockmax, o));
+        if ((tid & 31) == 0 && A.out_round_max)
+            atomicMax(A.out_round_max + round, f64_bits(blockmax));
+    }
+    if (A.stat_rechecks) {
+        for (int o = 16; o > 0; o >>= 1) rechecks += __shfl_xor_sync(FULL, rechecks, o);
+        if ((tid & 31) == 0 && rechecks) atomicAdd(A.stat_rechecks, rechecks);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// plain exact kernel: the reference's triple loop, one thread per candidate, no filter, no
+// shared memory.  Slow by design; used for UNB_OPT_EXACT_ONLY (validation of the filtered
+// kernels on the GPU itself) and for d too large for the tiled kernels.
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_exact(const ScanArgs A)
+{
+    const int round = blockIdx.y;
+    const int d = A.d;
+    const int n_live = A.round_nlive ? A.round_nlive[round] : A.n_live;
+    const long long n_items =
+        A.round_nitems ? (long long)A.round_nitems[round]
+                       : (A.n_items_dev ? (long long)*A.n_items_dev : A.n_items);
+    const int *items = A.item_idx ? A.item_idx + (A.round_item_off ? A.round_item_off[round] : 0)
+                                  : nullptr;
+    const int *lidx = A.live_idx ? A.live_idx + (A.round_live_off ? A.round_live_off[round] : 0)
+                                 : nullptr;
+    const long long item = (long long)blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const bool valid = item < n_items;
+    double best = 1e300;
+    if (valid) {
+        const long long row = items ? (long long)items[item] : item;
+        const long long orow = A.out_row_idx ? (long long)A.out_row_idx[item] : row;
+        const double *b = A.cand + row * d;
+        int first = -1, cnt = 0;
+        if (MODE == SCAN_SUBTRACT)
+            for (int k = 0; k < d; k++) A.out_rows[orow * d + k] = 0.0;
+        for (int i = 0; i < n_live; i++) {
+            const double *a = A.live_rows + (size_t)(lidx ? lidx[i] : i) * d;
+            double D = 0.0;
+            for (int k = 0; k < d; k++) D = sq_step(D, a[k], b[k]);
+            if (MODE == SCAN_MIN) {
+                best = fmin(best, D);
+            } else if (D <= A.r2) {
+                if (MODE == SCAN_FIND) { first = i; break; }
+                cnt++;
+                if (MODE == SCAN_SUBTRACT)
+                    for (int k = 0; k < d; k++) A.out_rows[orow * d + k] += a[k];
+            }
+        }
+        if (MODE == SCAN_FIND) {
+            if (A.out_idx) A.out_idx[orow] = first;
+            if (A.out_mask) A.out_mask[orow] = first >= 0;
+        } else if (MODE == SCAN_COUNT) {
+            A.out_idx[orow] = cnt;
+        } else if (MODE == SCAN_SUBTRACT) {
+            for (int k = 0; k < d; k++) {
+                double s = A.out_rows[orow * d + k];
+                A.out_rows[orow * d + k] = __dsub_rn(b[k], __ddiv_rn(s, (double)cnt));
+            }
+        } else if (A.out_min) {
+            A.out_min[orow] = best;
+        }
+    }
+    if (MODE == SCAN_MIN) {
+        double m = valid ? best : 0.0;
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+        if ((threadIdx.x & 31) == 0 && A.out_round_max)
+            atomicMax(A.out_round_max + round, f64_bits(m));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------
+template <typename K>
+int set_smem(unb_ctx *ctx, K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024)
+        UNB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)bytes));
+    return UNB_OK;
+}
+
+template <int DR, int TM, int MODE>
+int launch_reg(unb_ctx *ctx, const ScanArgs &a, int rounds, long long max_items, cudaStream_t s)
+{
+    const size_t smem = 128 + 2 * (size_t)(DR + 1) * REG_TILE_N * sizeof(double);
+    UNB_TRY(set_smem(ctx, k_scan_reg<DR, TM, MODE>, smem));
+    long long bx = (max_items + SCAN_THREADS * TM - 1) / (SCAN_THREADS * TM);
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)rounds);
+    k_scan_reg<DR, TM, MODE><<<grid, SCAN_THREADS, smem, s>>>(a);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+template <int DR, int MODE>
+int launch_reg_tm(unb_ctx *ctx, const ScanArgs &a, int rounds, long long max_items, cudaStream_t s)
+{
+    // candidates per thread: the LDS.128 : DFMA ratio is 1 : 2*TM, so TM >= 2 keeps the shared
+    // memory pipe below the DP pipe; tiny d affords 4.  SUBTRACT keeps TM=1 (its hit path
+    // read-modify-writes global rows), and small batches favour more blocks.
+    constexpr int TM_BIG = (DR <= 8) ? 4 : 2;
+    if constexpr (MODE == SCAN_SUBTRACT) {
+        return launch_reg<DR, 1, MODE>(ctx, a, rounds, max_items, s);
+    } else {
+        if (max_items * rounds < (long long)ctx->sm_count * SCAN_THREADS * 2 * TM_BIG)
+            return launch_reg<DR, 1, MODE>(ctx, a, rounds, max_items, s);
+        return launch_reg<DR, TM_BIG, MODE>(ctx, a, rounds, max_items, s);
+    }
+}
+
+template <int MODE>
+int launch_mode(unb_ctx *ctx, const ScanArgs &a, int rounds, long long max_items, cudaStream_t s)
+{
+    if (ctx->exact_only || a.tiles == nullptr) {
+        long long bx = (max_items + SCAN_THREADS - 1) / SCAN_THREADS;
+        if (bx < 1) bx = 1;
+        dim3 grid((unsigned)bx, (unsigned)rounds);
+        k_scan_exact<MODE><<<grid, SCAN_THREADS, 0, s>>>(a);
+        ctx->launches++;
+        UNB_CUDA(ctx, cudaGetLastError());
+        return UNB_OK;
+    }
+    if (a.dr <= 32 && a.tile_n == REG_TILE_N) {
+        switch (a.dr) {
+        case 4: return launch_reg_tm<4, MODE>(ctx, a, rounds, max_items, s);
+        case 8: return launch_reg_tm<8, MODE>(ctx, a, rounds, max_items, s);
+        case 12: return launch_reg_tm<12, MODE>(ctx, a, rounds, max_items, s);
+        case 16: return launch_reg_tm<16, MODE>(ctx, a, rounds, max_items, s);
+        case 20: return launch_reg_tm<20, MODE>(ctx, a, rounds, max_items, s);
+        case 24: return launch_reg_tm<24, MODE>(ctx, a, rounds, max_items, s);
+        case 28: return launch_reg_tm<28, MODE>(ctx, a, rounds, max_items, s);
+        case 32: return launch_reg_tm<32, MODE>(ctx, a, rounds, max_items, s);
+        default: break;
+        }
+    }
+    const size_t smem = 128 + ((size_t)a.dr * SCAN_THREADS + 2 * (size_t)(a.dr + 1) * a.tile_n) * sizeof(double);
+    UNB_TRY(set_smem(ctx, k_scan_gen<MODE>, smem));
+    long long bx = (max_items + SCAN_THREADS - 1) / SCAN_THREADS;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)rounds);
+    k_scan_gen<MODE><<<grid, SCAN_THREADS, smem, s>>>(a);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// exported (library-internal) entry points
+// ---------------------------------------------------------------------------------------
+double unb_kappa(size_t d) { return (8.0 * (double)d + 64.0) * 1.1102230246251565e-16; }
+
+// largest tile that lets the generic kernel keep 128 candidates + 2 tiles in 227 KB
+size_t unb_pick_tile_n(size_t d)
+{
+    size_t dr = (d + 3) / 4 * 4;
+    if (dr <= 32) return REG_TILE_N;
+    const size_t budget = 227 * 1024 - 128;
+    for (size_t tn = 64; tn >= 8; tn /= 2) {
+        size_t need = (dr * SCAN_THREADS + 2 * (dr + 1) * tn) * sizeof(double);
+        if (need <= budget) return tn;
+    }
+    return 0;   // does not fit: caller falls back to the plain exact kernel
+}
+
+int unb_live_build(unb_ctx *ctx, LiveTiles &L, const double *rows_dev, size_t n, size_t d,
+                   cudaStream_t s)
+{
+    L.valid = false;
+    L.n = n;
+    L.d = d;
+    L.dr = (d + 3) / 4 * 4;
+    L.tile_n = unb_pick_tile_n(d);
+    L.h_mode = HMODE_NONE;
+    UNB_TRY(unb_reserve(ctx, L.rows, (n ? n : 1) * d * sizeof(double)));
+    if (rows_dev != L.rows.p && n)
+        UNB_CUDA(ctx, cudaMemcpyAsync(L.rows.p, rows_dev, n * d * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, s));
+    UNB_TRY(unb_reserve(ctx, L.namax, sizeof(unsigned long long)));
+    UNB_CUDA(ctx, cudaMemsetAsync(L.namax.p, 0, sizeof(unsigned long long), s));
+    if (L.tile_n == 0 || n == 0) {   // plain exact kernels only
+        L.ntiles = 0;
+        L.valid = true;
+        return UNB_OK;
+    }
+    L.ntiles = (n + L.tile_n - 1) / L.tile_n;
+    const size_t slots = L.ntiles * L.tile_n;
+    UNB_TRY(unb_reserve(ctx, L.tiles, L.ntiles * (L.dr + 1) * L.tile_n * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, L.norms, slots * sizeof(double)));
+    k_live_build<<<(unsigned)((slots + 127) / 128), 128, 0, s>>>(
+        (const double *)L.rows.p, (int)n, (int)d, (int)L.dr, (int)L.tile_n, (int)L.ntiles,
+        (double *)L.tiles.p, (double *)L.norms.p);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    k_norm_max<<<8, 256, 0, s>>>((const double *)L.norms.p, (int)n,
+                                 (unsigned long long *)L.namax.p);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    L.valid = true;
+    return UNB_OK;
+}
+
+int unb_live_update_rows(unb_ctx *ctx, LiveTiles &L, const int *rows_dev_idx, size_t nrows,
+                         cudaStream_t s)
+{
+    if (!nrows || L.ntiles == 0) return UNB_OK;
+    k_live_update_rows<<<(unsigned)((nrows + 127) / 128), 128, 0, s>>>(
+        (const double *)L.rows.p, rows_dev_idx, (int)nrows, (int)L.d, (int)L.dr, (int)L.tile_n,
+        (double *)L.tiles.p, (double *)L.norms.p);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    UNB_CUDA(ctx, cudaMemsetAsync(L.namax.p, 0, sizeof(unsigned long long), s));
+    k_norm_max<<<8, 256, 0, s>>>((const double *)L.norms.p, (int)L.n,
+                                 (unsigned long long *)L.namax.p);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    L.h_mode = HMODE_NONE;   // h row of the touched slots is stale
+    return UNB_OK;
+}
+
+int unb_live_set_h(unb_ctx *ctx, LiveTiles &L, int h_mode, double r2, cudaStream_t s)
+{
+    if (L.ntiles == 0) return UNB_OK;
+    if (L.h_mode == h_mode && (h_mode == HMODE_MIN || L.h_r2 == r2)) return UNB_OK;
+    const size_t slots = L.ntiles * L.tile_n;
+    k_live_set_h<<<(unsigned)((slots + 127) / 128), 128, 0, s>>>(
+        (const double *)L.norms.p, (int)L.n, (int)L.dr, (int)L.tile_n, (int)L.ntiles, h_mode, r2,
+        unb_kappa(L.d), (double *)L.tiles.p);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    L.h_mode = h_mode;
+    L.h_r2 = r2;
+    return UNB_OK;
+}
+
+int unb_launch_gather_round_tiles(unb_ctx *ctx, const double *rows, int n, int d, int dr,
+                                  int tile_n, const int *idxA, const int *offA, const int *nA,
+                                  int rounds, long long round_tile_stride, double *tiles,
+                                  cudaStream_t s)
+{
+    const int max_tiles = (n + tile_n - 1) / tile_n;
+    dim3 grid((unsigned)((max_tiles * tile_n + 127) / 128), (unsigned)rounds);
+    k_gather_round_tiles<<<grid, 128, 0, s>>>(rows, d, dr, tile_n, idxA, offA, nA,
+                                              round_tile_stride, tiles);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+int unb_launch_scan(unb_ctx *ctx, int mode, const ScanArgs &a, int rounds, cudaStream_t s)
+{
+    if (a.n_items <= 0 || rounds <= 0) return UNB_OK;
+    switch (mode) {
+    case SCAN_FIND: return launch_mode<SCAN_FIND>(ctx, a, rounds, a.n_items, s);
+    case SCAN_COUNT: return launch_mode<SCAN_COUNT>(ctx, a, rounds, a.n_items, s);
+    case SCAN_SUBTRACT: return launch_mode<SCAN_SUBTRACT>(ctx, a, rounds, a.n_items, s);
+    case SCAN_MIN: return launch_mode<SCAN_MIN>(ctx, a, rounds, a.n_items, s);
+    default: return unb_fail(ctx, UNB_ERR_ARG, "unknown scan mode %d", mode);
+    }
+}
