@@ -147,8 +147,20 @@ class ClockSampler(object):
 _REF_STATE = {}
 
 
-def _ref_worker(chunk):
+def _ref_init():
+    """Worker start-up: one BLAS thread per worker (the workers are the parallelism)."""
+    try:
+        import threadpoolctl
+        _REF_STATE["blas_limit"] = threadpoolctl.threadpool_limits(1)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def _ref_worker(i):
+    """One worker's share of a step: the reference's own calls on its rows (inherited by fork,
+    nothing is pickled but the index)."""
     region = _REF_STATE["region"]
+    chunk = _REF_STATE["chunks"][i]
     m = region.inside(chunk)
     like = numpy_loglike(chunk[m])
     return int(m.sum()), float(like.sum()) if len(like) else 0.0
@@ -205,17 +217,15 @@ def reference_throughput(steps, warmup, rows_per_core=65536, cores=None):
     import multiprocessing as mp
     region, kind = reference_setup()
     cores = cores or len(os.sched_getaffinity(0))
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     sample_rows = rows_per_core * cores
     cand = make_candidates(region, sample_rows, 3)
-    chunks = np.array_split(cand, cores)
+    _REF_STATE["chunks"] = np.array_split(cand, cores)
     ctx = mp.get_context("fork")
     times = []
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_ref_init) as pool:
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            res = pool.map(_ref_worker, chunks)
+            res = pool.map(_ref_worker, range(cores), chunksize=1)
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
@@ -286,8 +296,12 @@ def run_ours(args):
     kind, lparams = loglike.device_spec(NDIM)
     region._bind()
 
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream: the kernels are launched on it and the CUDA events that
+    # time them are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sh = ctypes.c_void_p(stream.cuda_stream)
+    assert sh.value, "need a non-default stream handle"
     pts_dev = torch.from_numpy(cand).cuda()
     mask_dev = torch.empty(M, dtype=torch.uint8, device="cuda")
     like_dev = torch.empty(M, dtype=torch.float64, device="cuda")
