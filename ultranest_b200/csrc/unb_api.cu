@@ -631,8 +631,8 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     const size_t d = R.live.d;
     UNB_TRY(unb_reserve(ctx, ln.tcand, m * d * sizeof(double)));
     UNB_TRY(unb_reserve(ctx, ln.items, m * sizeof(int)));
-    UNB_TRY(unb_reserve(ctx, ln.counter, sizeof(int)));
-    UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, sizeof(int), s));
+    UNB_TRY(unb_reserve(ctx, ln.counter, 2 * sizeof(int)));   // [0] survivors, [1] work-queue head
+    UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 2 * sizeof(int), s));
     if (idx_dev) UNB_CUDA(ctx, cudaMemsetAsync(idx_dev, 0xff, m * sizeof(long long), s));
     PrepArgs p;
     memset(&p, 0, sizeof(p));
@@ -658,7 +658,10 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     a.r2 = R.r2;
     a.out_mask = mask_dev;
     a.out_idx = idx_dev;
-    UNB_TRY(unb_launch_scan(ctx, SCAN_FIND, a, 1, s));
+    if (idx_dev)   // first-neighbour index wanted: ordered scan
+        UNB_TRY(unb_launch_scan(ctx, SCAN_FIND, a, 1, s));
+    else           // mask only: persistent any-neighbour kernel
+        UNB_TRY(unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s));
     if (like_dev && loglike_kind != UNB_LOGLIKE_NONE)
         UNB_TRY(unb_launch_loglike(ctx, loglike_kind, pts_dev, (int)d, (long long)m, like_dev,
                                    mask_dev, (const double *)ctx->lparams.p, s));

@@ -175,6 +175,7 @@ int unb_live_set_h(unb_ctx *ctx, LiveTiles &L, int h_mode, double r2, cudaStream
 double unb_kappa(size_t d);
 size_t unb_pick_tile_n(size_t d);
 int unb_launch_scan(unb_ctx *ctx, int mode, const ScanArgs &a, int rounds, cudaStream_t s);
+int unb_launch_inside_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s);
 int unb_launch_gather_round_tiles(unb_ctx *ctx, const double *rows, int n, int d, int dr,
                                   int tile_n, const int *idxA, const int *offA,
                                   const int *nA, int rounds, long long round_tile_stride,

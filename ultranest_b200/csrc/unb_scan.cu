@@ -382,6 +382,182 @@ __global__ void __launch_bounds__(SCAN_THREADS, reg_min_blocks(DR, TM)) k_scan_r
 }
 
 // ---------------------------------------------------------------------------------------
+// membership ("any neighbour") kernel for MLFriends.inside: persistent blocks + slot refill
+//
+// inside() only needs to know WHETHER a live point lies within the radius, not which one comes
+// first, so the scan order is free.  Each block streams the live tiles round-robin for as long as
+// there is work; every thread owns TM candidate slots; a slot is retired at the first tile
+// boundary after its candidate found a neighbour (or has seen all ntiles tiles) and is
+// immediately refilled from a global work queue, so no lane idles while its warp-mates are
+// still searching (the ordered kernel above pays the warp-maximum of the first-hit positions).
+// Decisions are still made by the exact reference arithmetic, so the mask is bit-identical.
+// ---------------------------------------------------------------------------------------
+template <int DR, int TM>
+__global__ void __launch_bounds__(SCAN_THREADS, reg_min_blocks(DR, TM))
+k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    constexpr int TILE_DOUBLES = (DR + 1) * REG_TILE_N;
+    constexpr uint32_t TILE_BYTES = TILE_DOUBLES * sizeof(double);
+    double *tbuf = reinterpret_cast<double *>(smem_raw + 128);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const double *tiles = A.tiles;
+    const int ntiles = (A.n_live + REG_TILE_N - 1) / REG_TILE_N;
+    const int n_items = A.n_items_dev ? *A.n_items_dev : (int)A.n_items;
+    const int d = A.d;
+    const double thr_scale = __dmul_rn(0.5, __dsub_rn(1.0, A.kappa));
+
+    double a[TM][DR];
+    int row[TM], orow[TM], rem[TM], thrkey[TM], hit[TM];
+#pragma unroll
+    for (int m = 0; m < TM; m++) {
+        row[m] = -1; orow[m] = -1; rem[m] = 0; thrkey[m] = INT_MAX; hit[m] = 0;
+#pragma unroll
+        for (int k = 0; k < DR; k++) a[m][k] = 0.0;
+    }
+    bool exhausted = false;
+
+    // retire finished slots and refill every free slot from the queue (warp-synchronous)
+    auto refill = [&]() {
+#pragma unroll
+        for (int m = 0; m < TM; m++) {
+            if (row[m] >= 0 && (hit[m] || rem[m] <= 0)) {
+                A.out_mask[orow[m]] = hit[m] ? 1 : 0;
+                row[m] = -1;
+                thrkey[m] = INT_MAX;
+            }
+            const bool need = (row[m] < 0) && !exhausted;
+            const unsigned ball = __ballot_sync(FULL, need);
+            if (ball) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(queue_head, __popc(ball));
+                base = __shfl_sync(FULL, base, 0);
+                if (need) {
+                    const int item = base + __popc(ball & ((1u << lane) - 1));
+                    if (item < n_items) {
+                        const int r = A.item_idx ? A.item_idx[item] : item;
+                        row[m] = r;
+                        orow[m] = A.out_row_idx ? A.out_row_idx[item] : r;
+                        double nb = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DR; k++) {
+                            const double v = (k < d) ? A.cand[(size_t)r * d + k] : 0.0;
+                            a[m][k] = v;
+                            nb = fma(v, v, nb);
+                        }
+                        thrkey[m] = __double2hiint(__dmul_rn(nb, thr_scale)) - 1;
+                        rem[m] = ntiles;
+                        hit[m] = 0;
+                    } else {
+                        exhausted = true;
+                    }
+                }
+            }
+        }
+        // one lane learning that the queue is empty is enough for the whole warp
+        exhausted = __any_sync(FULL, exhausted);
+    };
+
+    refill();
+    {
+        bool idle = true;
+#pragma unroll
+        for (int m = 0; m < TM; m++) idle &= row[m] < 0;
+        if (__syncthreads_and(idle)) return;   // nothing claimed by this block
+    }
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
+        tma_bulk_g2s(tbuf, tiles, TILE_BYTES, &bars[0]);
+        mbar_arrive_expect_tx(&bars[1], TILE_BYTES);
+        tma_bulk_g2s(tbuf + TILE_DOUBLES, tiles + (size_t)(1 % ntiles) * TILE_DOUBLES, TILE_BYTES,
+                     &bars[1]);
+    }
+
+    unsigned long long rechecks = 0;
+    for (unsigned tt = 0;; tt++) {
+        const int buf = tt & 1;
+        mbar_wait(&bars[buf], (tt >> 1) & 1);
+        const double *T = tbuf + buf * TILE_DOUBLES;
+#pragma unroll 1
+        for (int g = 0; g < REG_TILE_N / TN; g++) {
+            const double *Tg = T + g * TN;
+            double acc[TM][TN];
+            {
+                const double4 h = *reinterpret_cast<const double4 *>(Tg + DR * REG_TILE_N);
+#pragma unroll
+                for (int m = 0; m < TM; m++) {
+                    acc[m][0] = h.x; acc[m][1] = h.y; acc[m][2] = h.z; acc[m][3] = h.w;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < DR; k++) {
+                const double4 b = *reinterpret_cast<const double4 *>(Tg + k * REG_TILE_N);
+#pragma unroll
+                for (int m = 0; m < TM; m++) {
+                    acc[m][0] = fma(a[m][k], b.x, acc[m][0]);
+                    acc[m][1] = fma(a[m][k], b.y, acc[m][1]);
+                    acc[m][2] = fma(a[m][k], b.z, acc[m][2]);
+                    acc[m][3] = fma(a[m][k], b.w, acc[m][3]);
+                }
+            }
+            bool any = false;
+#pragma unroll
+            for (int m = 0; m < TM; m++)
+#pragma unroll
+                for (int n = 0; n < TN; n++) any |= __double2hiint(acc[m][n]) >= thrkey[m];
+            if (any) {
+#pragma unroll
+                for (int m = 0; m < TM; m++) {
+#pragma unroll
+                    for (int n = 0; n < TN; n++) {
+                        if (__double2hiint(acc[m][n]) >= thrkey[m]) {
+                            rechecks++;
+                            const double D = exact_dist_reg<DR>(a[m], Tg + n);
+                            if (D <= A.r2) {
+                                hit[m] = 1;
+                                thrkey[m] = INT_MAX;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < TM; m++) rem[m]--;
+        refill();
+        bool idle = true;
+#pragma unroll
+        for (int m = 0; m < TM; m++) idle &= row[m] < 0;
+        const bool all_idle = __syncthreads_and(idle);
+        if (all_idle) {
+            // tile tt+1 is always in flight
+            mbar_wait(&bars[(tt + 1) & 1], ((tt + 1) >> 1) & 1);
+            break;
+        }
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bars[buf], TILE_BYTES);
+            tma_bulk_g2s(tbuf + buf * TILE_DOUBLES,
+                         tiles + (size_t)((tt + 2) % (unsigned)ntiles) * TILE_DOUBLES, TILE_BYTES,
+                         &bars[buf]);
+        }
+    }
+    if (A.stat_rechecks) {
+        for (int o = 16; o > 0; o >>= 1) rechecks += __shfl_xor_sync(FULL, rechecks, o);
+        if (lane == 0 && rechecks) atomicAdd(A.stat_rechecks, rechecks);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // generic kernel: any d that fits shared memory; candidates k-major in shared memory,
 // one candidate per thread, 8 live points per register group
 // ---------------------------------------------------------------------------------------
@@ -686,7 +862,57 @@ int launch_mode(unb_ctx *ctx, const ScanArgs &a, int rounds, long long max_items
     return UNB_OK;
 }
 
+template <int DR, int TM>
+int launch_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
+{
+    const size_t smem = 128 + 2 * (size_t)(DR + 1) * REG_TILE_N * sizeof(double);
+    UNB_TRY(set_smem(ctx, k_inside_any<DR, TM>, smem));
+    int per_sm = 0;
+    UNB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inside_any<DR, TM>,
+                                                               SCAN_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long bx = (a.n_items + SCAN_THREADS * TM - 1) / (SCAN_THREADS * TM);
+    const long long resident = (long long)per_sm * ctx->sm_count;
+    if (bx > resident) bx = resident;
+    if (bx < 1) bx = 1;
+    k_inside_any<DR, TM><<<(unsigned)bx, SCAN_THREADS, smem, s>>>(a, queue_head);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+template <int DR>
+int launch_any_tm(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
+{
+    constexpr int TM_BIG = (DR <= 8) ? 4 : 2;
+    if (a.n_items < (long long)ctx->sm_count * SCAN_THREADS * 2 * TM_BIG)
+        return launch_any<DR, 1>(ctx, a, queue_head, s);
+    return launch_any<DR, TM_BIG>(ctx, a, queue_head, s);
+}
+
 }  // namespace
+
+// membership-only scan (mask, no index): persistent refill kernel when the shape allows,
+// else the ordered FIND kernel.  queue_head must be a zeroed device int.
+int unb_launch_inside_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
+{
+    if (a.n_items <= 0) return UNB_OK;
+    if (!ctx->exact_only && a.tiles && a.dr <= 32 && a.tile_n == REG_TILE_N && a.out_mask &&
+        !a.out_idx && a.n_live > 0) {
+        switch (a.dr) {
+        case 4: return launch_any_tm<4>(ctx, a, queue_head, s);
+        case 8: return launch_any_tm<8>(ctx, a, queue_head, s);
+        case 12: return launch_any_tm<12>(ctx, a, queue_head, s);
+        case 16: return launch_any_tm<16>(ctx, a, queue_head, s);
+        case 20: return launch_any_tm<20>(ctx, a, queue_head, s);
+        case 24: return launch_any_tm<24>(ctx, a, queue_head, s);
+        case 28: return launch_any_tm<28>(ctx, a, queue_head, s);
+        case 32: return launch_any_tm<32>(ctx, a, queue_head, s);
+        default: break;
+        }
+    }
+    return unb_launch_scan(ctx, SCAN_FIND, a, 1, s);
+}
 
 // ---------------------------------------------------------------------------------------
 // exported (library-internal) entry points
