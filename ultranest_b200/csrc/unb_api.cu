@@ -560,6 +560,7 @@ extern "C" int unb_region_set_layer(unb_ctx *ctx, int kind, const double *shift,
             return UNB_OK;   // unchanged since the last call
         R.layer_shift_h.assign(shift, shift + ndim);
         R.layer_mat_h.assign(mat, mat + mat_n);
+        R.param_version++;
         UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
         UNB_TRY(unb_reserve(ctx, R.layer_shift, ndim * sizeof(double)));
         UNB_TRY(unb_reserve(ctx, R.layer_mat, mat_n * sizeof(double)));
@@ -567,6 +568,7 @@ extern "C" int unb_region_set_layer(unb_ctx *ctx, int kind, const double *shift,
         UNB_TRY(h2d(ctx, R.layer_mat.p, mat, mat_n * sizeof(double), s));
         UNB_CUDA(ctx, cudaStreamSynchronize(s));
     }
+    if (R.layer_kind != kind) R.param_version++;
     R.layer_kind = kind;
     R.layer_d = ndim;
     return UNB_OK;
@@ -586,6 +588,7 @@ extern "C" int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, cons
         return UNB_OK;   // unchanged since the last call
     R.ell_center_h.assign(center, center + ndim);
     R.ell_invcov_h.assign(invcov, invcov + ndim * ndim);
+    R.param_version++;
     UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
     UNB_TRY(unb_reserve(ctx, R.ell_center, ndim * sizeof(double)));
     UNB_TRY(unb_reserve(ctx, R.ell_invcov, ndim * ndim * sizeof(double)));
@@ -634,6 +637,11 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     UNB_TRY(unb_reserve(ctx, ln.counter, 2 * sizeof(int)));   // [0] survivors, [1] work-queue head
     UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 2 * sizeof(int), s));
     if (idx_dev) UNB_CUDA(ctx, cudaMemsetAsync(idx_dev, 0xff, m * sizeof(long long), s));
+    // mask-only requests on a tiled live block go through the register prep kernel (constant
+    // memory parameters, fused likelihood) and the persistent any-neighbour kernel
+    const bool use_any = !ctx->exact_only && !idx_dev && R.live.ntiles > 0 && R.live.dr <= 32;
+    const bool fuse_like = use_any && like_dev && loglike_kind != UNB_LOGLIKE_NONE;
+    if (use_any) UNB_TRY(unb_prep_sync_constants(ctx, s));
     PrepArgs p;
     memset(&p, 0, sizeof(p));
     p.pts = pts_dev;
@@ -649,6 +657,12 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     p.tcand = (double *)ln.tcand.p;
     p.items = (int *)ln.items.p;
     p.n_items = (int *)ln.counter.p;
+    p.use_constants = use_any ? 1 : 0;
+    if (fuse_like) {
+        p.like = like_dev;
+        p.loglike_kind = loglike_kind;
+        p.lparams = (const double *)ctx->lparams.p;
+    }
     UNB_TRY(unb_launch_prep(ctx, p, s));
     ScanArgs a = scan_args_for(R.live);
     a.cand = (const double *)ln.tcand.p;
@@ -658,11 +672,13 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     a.r2 = R.r2;
     a.out_mask = mask_dev;
     a.out_idx = idx_dev;
-    if (idx_dev)   // first-neighbour index wanted: ordered scan
-        UNB_TRY(unb_launch_scan(ctx, SCAN_FIND, a, 1, s));
-    else           // mask only: persistent any-neighbour kernel
+    if (use_any) {
+        a.out_like = fuse_like ? like_dev : nullptr;
         UNB_TRY(unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s));
-    if (like_dev && loglike_kind != UNB_LOGLIKE_NONE)
+    } else {
+        UNB_TRY(unb_launch_scan(ctx, SCAN_FIND, a, 1, s));
+    }
+    if (like_dev && loglike_kind != UNB_LOGLIKE_NONE && !fuse_like)
         UNB_TRY(unb_launch_loglike(ctx, loglike_kind, pts_dev, (int)d, (long long)m, like_dev,
                                    mask_dev, (const double *)ctx->lparams.p, s));
     return UNB_OK;
@@ -705,7 +721,7 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
     const size_t rowb = d * sizeof(double);
     UNB_TRY(unb_live_set_h(ctx, R.live, HMODE_THRESH, R.r2, S0(ctx)));
     UNB_CUDA(ctx, cudaStreamSynchronize(S0(ctx)));
-    size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 17);
+    size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18);
     if (chunk > m) chunk = m;
     const bool src_pinned = host_is_pinned(pts);
     const bool mask_pinned = host_is_pinned(mask);
@@ -855,7 +871,12 @@ extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, 
     a.r2 = ctx->region.r2;
     a.out_idx = (long long *)nnearby_dev;
     a.out_mask = mask_dev;
-    return unb_launch_scan(ctx, SCAN_FIND, a, 1, s);
+    if (nnearby_dev) return unb_launch_scan(ctx, SCAN_FIND, a, 1, s);
+    // mask only: the persistent any-neighbour kernel MLFriends.inside uses
+    Lane &ln = ctx->lane[0];
+    UNB_TRY(unb_reserve(ctx, ln.counter, 2 * sizeof(int)));
+    UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 2 * sizeof(int), s));
+    return unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s);
 }
 
 extern "C" int unb_region_count_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby)

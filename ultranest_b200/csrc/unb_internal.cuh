@@ -107,6 +107,7 @@ struct ScanArgs {
     unsigned char *out_mask;  // FIND: idx >= 0                               (nullable)
     double *out_rows;         // SUBTRACT: (M x d) result rows
     double *out_min;          // MIN: per-candidate exact min distance        (nullable)
+    double *out_like;         // any-kernel: rows without a neighbour get -inf (nullable)
     unsigned long long *out_round_max;   // MIN: per-round max over candidates (ordered bits)
     unsigned long long *stat_rechecks;   // diagnostic counter (nullable)
 };
@@ -127,6 +128,7 @@ struct RegionState {
     DevBuf ell_center, ell_invcov;
     bool have_radius = false;
     double r2 = 0.0;
+    long long param_version = 0;   // bumped whenever layer / ellipsoid parameters change
 };
 
 // one in-flight chunk of a host-buffer call: its own stream, device scratch and pinned staging,
@@ -196,7 +198,13 @@ struct PrepArgs {
     double *tcand;            // out: compacted transformed rows
     int *items;               // out: original row of each compacted row
     int *n_items;             // in/out: device counter (must be zeroed)
+    // register kernel (d <= 32) only:
+    int use_constants;        // ellipsoid / layer parameters come from __constant__ memory
+    double *like;             // out: fused likelihood of the rows inside the ellipsoid (nullable)
+    int loglike_kind;
+    const double *lparams;    // device likelihood parameter block
 };
+int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s);
 int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s);
 int unb_launch_transform(unb_ctx *ctx, int kind, bool inverse, const double *in, long long m,
                          int d, const double *shift, const double *mat, double *out,

@@ -94,6 +94,110 @@ __global__ void k_prep(const PrepArgs P)
 }
 
 // ---------------------------------------------------------------------------------------
+// register variant for d <= 32: the candidate lives in registers and the region's matrices in
+// __constant__ memory, so every multiply takes its matrix operand straight from the constant
+// bank (no load instruction at all).  Matrices are stored with row stride DR (d rounded up to
+// 4) and zero padding; padded terms add +0 and leave the reference's sequence unchanged.
+// Optionally fuses the vectorised likelihood of the rows that pass the ellipsoid, so the
+// proposals are read from HBM exactly once.
+// ---------------------------------------------------------------------------------------
+constexpr int PREP_MAXD = 32;
+__constant__ double c_ell_center[PREP_MAXD];
+__constant__ double c_ell_invcov[PREP_MAXD * PREP_MAXD];
+__constant__ double c_xf_shift[PREP_MAXD];
+__constant__ double c_xf_mat[PREP_MAXD * PREP_MAXD];
+
+__device__ double np_pairwise_sum(const double *a, int n);
+
+__device__ __forceinline__ double loglike_row(int kind, const double *p, int d, double *t,
+                                              const double *lp)
+{
+    if (kind == UNB_LOGLIKE_GAUSS) {
+        const double sigma = __ldg(lp + d), norm_const = __ldg(lp + d + 1);
+        for (int i = 0; i < d; i++) {
+            double z = __ddiv_rn(__dsub_rn(p[i], __ldg(lp + i)), sigma);
+            t[i] = __dmul_rn(z, z);
+        }
+        return __dsub_rn(__dmul_rn(-0.5, np_pairwise_sum(t, d)), norm_const);
+    } else if (kind == UNB_LOGLIKE_ROSENBROCK) {
+        for (int i = 0; i + 1 < d; i++) {
+            const double a = p[i], b = p[i + 1];
+            const double u = __dsub_rn(b, __dmul_rn(a, a));
+            const double v = __dsub_rn(1.0, a);
+            t[i] = __dadd_rn(__dmul_rn(100.0, __dmul_rn(u, u)), __dmul_rn(v, v));
+        }
+        return __dmul_rn(-2.0, np_pairwise_sum(t, d - 1));
+    }
+    double chi = 1.0;   // eggbox
+    for (int i = 0; i < d; i++) chi = __dmul_rn(chi, cos(__ddiv_rn(p[i], 2.0)));
+    return pow(__dadd_rn(2.0, chi), 5.0);
+}
+
+template <int DR>
+__global__ void __launch_bounds__(128) k_prep_reg(const PrepArgs P)
+{
+    extern __shared__ __align__(16) double rowbuf[];
+    const int d = P.d;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = j < P.m;
+    double p[DR];
+#pragma unroll
+    for (int k = 0; k < DR; k++) p[k] = (valid && k < d) ? P.pts[j * d + k] : 0.0;
+    bool inside = valid;
+    if (P.center) {
+        double dl[DR];
+#pragma unroll
+        for (int k = 0; k < DR; k++) dl[k] = __dsub_rn(p[k], c_ell_center[k]);
+        double acc = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < DR; jj++)
+#pragma unroll
+            for (int k = 0; k < DR; k++)
+                acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dl[jj], c_ell_invcov[jj * DR + k]), dl[k]));
+        inside = valid && (acc <= P.r2);
+        if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
+    }
+    if (P.like && valid) {
+        double like = -__longlong_as_double(0x7ff0000000000000LL);
+        if (inside) {
+            double *t = rowbuf + (size_t)threadIdx.x * odd_stride(d);
+            like = loglike_row(P.loglike_kind, P.pts + j * d, d, t, P.lparams);
+        }
+        P.like[j] = like;
+    }
+    if (P.layer_kind < 0) return;
+
+    const unsigned ball = __ballot_sync(FULL, inside);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && ball) base = atomicAdd(P.n_items, __popc(ball));
+    base = __shfl_sync(FULL, base, 0);
+    if (!inside) return;
+    const int pos = base + __popc(ball & ((1u << (threadIdx.x & 31)) - 1));
+    P.items[pos] = (int)j;
+    double *out = P.tcand + (size_t)pos * d;
+    if (P.layer_kind == UNB_LAYER_AFFINE) {
+        double x[DR];
+#pragma unroll
+        for (int k = 0; k < DR; k++) x[k] = __dsub_rn(p[k], c_xf_shift[k]);
+#pragma unroll
+        for (int jj = 0; jj < DR; jj++) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < DR; k++) t = fma(x[k], c_xf_mat[k * DR + jj], t);
+            if (jj < d) out[jj] = t;
+        }
+    } else if (P.layer_kind == UNB_LAYER_SCALING) {
+#pragma unroll
+        for (int k = 0; k < DR; k++)
+            if (k < d) out[k] = __ddiv_rn(__dsub_rn(p[k], c_xf_shift[k]), c_xf_mat[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < DR; k++)
+            if (k < d) out[k] = p[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // layer transforms
 // ---------------------------------------------------------------------------------------
 __global__ void k_transform(int kind, int inverse, const double *__restrict__ in, long long m,
@@ -212,27 +316,7 @@ __global__ void k_loglike(int kind, const double *__restrict__ params, int d, lo
         like[j] = -__longlong_as_double(0x7ff0000000000000LL);
         return;
     }
-    const double *p = params + j * d;
-    if (kind == UNB_LOGLIKE_GAUSS) {
-        const double sigma = __ldg(lp + d), norm_const = __ldg(lp + d + 1);
-        for (int i = 0; i < d; i++) {
-            double z = __ddiv_rn(__dsub_rn(p[i], __ldg(lp + i)), sigma);
-            t[i] = __dmul_rn(z, z);
-        }
-        like[j] = __dsub_rn(__dmul_rn(-0.5, np_pairwise_sum(t, d)), norm_const);
-    } else if (kind == UNB_LOGLIKE_ROSENBROCK) {
-        for (int i = 0; i + 1 < d; i++) {
-            const double a = p[i], b = p[i + 1];
-            const double u = __dsub_rn(b, __dmul_rn(a, a));
-            const double v = __dsub_rn(1.0, a);
-            t[i] = __dadd_rn(__dmul_rn(100.0, __dmul_rn(u, u)), __dmul_rn(v, v));
-        }
-        like[j] = __dmul_rn(-2.0, np_pairwise_sum(t, d - 1));
-    } else {   // eggbox
-        double chi = 1.0;
-        for (int i = 0; i < d; i++) chi = __dmul_rn(chi, cos(__ddiv_rn(p[i], 2.0)));
-        like[j] = pow(__dadd_rn(2.0, chi), 5.0);
-    }
+    like[j] = loglike_row(kind, params + j * d, d, t, lp);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -305,9 +389,78 @@ __global__ void k_pairdist(const double *__restrict__ pts, const long long *__re
 
 size_t unb_max_rowwise_d() { return ROW_SMEM_BUDGET / sizeof(double) / 32 - 1; }
 
+// -- __constant__ parameter block of the register prep kernel -------------------------------
+static const unb_ctx *g_const_owner = nullptr;
+static long long g_const_version = -1;
+
+static int upload_padded(unb_ctx *ctx, const void *symbol, const std::vector<double> &src,
+                         size_t rows, size_t cols, size_t stride, cudaStream_t s)
+{
+    std::vector<double> buf(rows * stride, 0.0);
+    for (size_t r = 0; r < rows; r++)
+        for (size_t c = 0; c < cols; c++) buf[r * stride + c] = src[r * cols + c];
+    UNB_CUDA(ctx, cudaMemcpyToSymbolAsync(symbol, buf.data(), buf.size() * sizeof(double), 0,
+                                          cudaMemcpyHostToDevice, s));
+    return UNB_OK;
+}
+
+// (re)load the region's ellipsoid / layer parameters into constant memory if they changed
+int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s)
+{
+    RegionState &R = ctx->region;
+    if (g_const_owner == ctx && g_const_version == R.param_version) return UNB_OK;
+    const size_t d = R.live.d;
+    if (d > (size_t)PREP_MAXD) return UNB_OK;
+    const size_t dr = (d + 3) / 4 * 4;
+    // kernels of either lane may still read the old values
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+    if (R.have_ellipsoid && R.ell_d == d) {
+        UNB_TRY(upload_padded(ctx, c_ell_center, R.ell_center_h, 1, d, dr, s));
+        UNB_TRY(upload_padded(ctx, c_ell_invcov, R.ell_invcov_h, d, d, dr, s));
+    }
+    if (R.layer_kind == UNB_LAYER_AFFINE && R.layer_d == d) {
+        UNB_TRY(upload_padded(ctx, c_xf_shift, R.layer_shift_h, 1, d, dr, s));
+        UNB_TRY(upload_padded(ctx, c_xf_mat, R.layer_mat_h, d, d, dr, s));
+    } else if (R.layer_kind == UNB_LAYER_SCALING && R.layer_d == d) {
+        UNB_TRY(upload_padded(ctx, c_xf_shift, R.layer_shift_h, 1, d, dr, s));
+        std::vector<double> ones(dr, 1.0);
+        for (size_t k = 0; k < d; k++) ones[k] = R.layer_mat_h[k];
+        UNB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_xf_mat, ones.data(), dr * sizeof(double), 0,
+                                              cudaMemcpyHostToDevice, s));
+    }
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    g_const_owner = ctx;
+    g_const_version = R.param_version;
+    return UNB_OK;
+}
+
+template <int DR>
+static int launch_prep_reg(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s)
+{
+    const size_t smem = p.like ? (size_t)128 * odd_stride(p.d) * sizeof(double) : 0;
+    k_prep_reg<DR><<<(unsigned)((p.m + 127) / 128), 128, smem, s>>>(p);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
 int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s)
 {
     if (p.m <= 0) return UNB_OK;
+    if (p.use_constants && p.d <= PREP_MAXD) {
+        switch ((p.d + 3) / 4 * 4) {
+        case 4: return launch_prep_reg<4>(ctx, p, s);
+        case 8: return launch_prep_reg<8>(ctx, p, s);
+        case 12: return launch_prep_reg<12>(ctx, p, s);
+        case 16: return launch_prep_reg<16>(ctx, p, s);
+        case 20: return launch_prep_reg<20>(ctx, p, s);
+        case 24: return launch_prep_reg<24>(ctx, p, s);
+        case 28: return launch_prep_reg<28>(ctx, p, s);
+        case 32: return launch_prep_reg<32>(ctx, p, s);
+        default: break;
+        }
+    }
     const int threads = row_threads(p.d);
     if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%d too large for the row kernels", p.d);
     const size_t smem = (size_t)threads * odd_stride(p.d) * sizeof(double);

@@ -426,6 +426,7 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
         for (int m = 0; m < TM; m++) {
             if (row[m] >= 0 && (hit[m] || rem[m] <= 0)) {
                 A.out_mask[orow[m]] = hit[m] ? 1 : 0;
+                if (A.out_like && !hit[m]) A.out_like[orow[m]] = -pos_inf();
                 row[m] = -1;
                 thrkey[m] = INT_MAX;
             }
@@ -484,60 +485,64 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
     }
 
     unsigned long long rechecks = 0;
+    bool warp_idle = false;   // a warp with no live slot skips the tile (drain phase)
     for (unsigned tt = 0;; tt++) {
         const int buf = tt & 1;
         mbar_wait(&bars[buf], (tt >> 1) & 1);
         const double *T = tbuf + buf * TILE_DOUBLES;
+        if (!warp_idle) {
 #pragma unroll 1
-        for (int g = 0; g < REG_TILE_N / TN; g++) {
-            const double *Tg = T + g * TN;
-            double acc[TM][TN];
-            {
-                const double4 h = *reinterpret_cast<const double4 *>(Tg + DR * REG_TILE_N);
+            for (int g = 0; g < REG_TILE_N / TN; g++) {
+                const double *Tg = T + g * TN;
+                double acc[TM][TN];
+                {
+                    const double4 h = *reinterpret_cast<const double4 *>(Tg + DR * REG_TILE_N);
 #pragma unroll
-                for (int m = 0; m < TM; m++) {
-                    acc[m][0] = h.x; acc[m][1] = h.y; acc[m][2] = h.z; acc[m][3] = h.w;
+                    for (int m = 0; m < TM; m++) {
+                        acc[m][0] = h.x; acc[m][1] = h.y; acc[m][2] = h.z; acc[m][3] = h.w;
+                    }
                 }
-            }
 #pragma unroll
-            for (int k = 0; k < DR; k++) {
-                const double4 b = *reinterpret_cast<const double4 *>(Tg + k * REG_TILE_N);
+                for (int k = 0; k < DR; k++) {
+                    const double4 b = *reinterpret_cast<const double4 *>(Tg + k * REG_TILE_N);
 #pragma unroll
-                for (int m = 0; m < TM; m++) {
-                    acc[m][0] = fma(a[m][k], b.x, acc[m][0]);
-                    acc[m][1] = fma(a[m][k], b.y, acc[m][1]);
-                    acc[m][2] = fma(a[m][k], b.z, acc[m][2]);
-                    acc[m][3] = fma(a[m][k], b.w, acc[m][3]);
+                    for (int m = 0; m < TM; m++) {
+                        acc[m][0] = fma(a[m][k], b.x, acc[m][0]);
+                        acc[m][1] = fma(a[m][k], b.y, acc[m][1]);
+                        acc[m][2] = fma(a[m][k], b.z, acc[m][2]);
+                        acc[m][3] = fma(a[m][k], b.w, acc[m][3]);
+                    }
                 }
-            }
-            bool any = false;
+                bool any = false;
 #pragma unroll
-            for (int m = 0; m < TM; m++)
+                for (int m = 0; m < TM; m++)
 #pragma unroll
-                for (int n = 0; n < TN; n++) any |= __double2hiint(acc[m][n]) >= thrkey[m];
-            if (any) {
+                    for (int n = 0; n < TN; n++) any |= __double2hiint(acc[m][n]) >= thrkey[m];
+                if (any) {
 #pragma unroll
-                for (int m = 0; m < TM; m++) {
+                    for (int m = 0; m < TM; m++) {
 #pragma unroll
-                    for (int n = 0; n < TN; n++) {
-                        if (__double2hiint(acc[m][n]) >= thrkey[m]) {
-                            rechecks++;
-                            const double D = exact_dist_reg<DR>(a[m], Tg + n);
-                            if (D <= A.r2) {
-                                hit[m] = 1;
-                                thrkey[m] = INT_MAX;
+                        for (int n = 0; n < TN; n++) {
+                            if (__double2hiint(acc[m][n]) >= thrkey[m]) {
+                                rechecks++;
+                                const double D = exact_dist_reg<DR>(a[m], Tg + n);
+                                if (D <= A.r2) {
+                                    hit[m] = 1;
+                                    thrkey[m] = INT_MAX;
+                                }
                             }
                         }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int m = 0; m < TM; m++) rem[m]--;
-        refill();
+            for (int m = 0; m < TM; m++) rem[m]--;
+            refill();
+        }
         bool idle = true;
 #pragma unroll
         for (int m = 0; m < TM; m++) idle &= row[m] < 0;
+        warp_idle = __all_sync(FULL, idle);
         const bool all_idle = __syncthreads_and(idle);
         if (all_idle) {
             // tile tt+1 is always in flight
