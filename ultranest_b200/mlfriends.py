@@ -447,6 +447,41 @@ def _rewind_rounds(rng, state, npoints, rounds_consumed):
         rng.randint(npoints, size=npoints)
 
 
+def _bootstrap_rounds(u, unormed, selected, lo, hi, minvol):
+    """Rounds ``lo <= r < hi`` of the MLFriends bootstrap: per-round radius^2 (float32-rounded
+    like the reference) and enlargement.  Host: d x d ``bounding_ellipsoid`` / ``inv`` of each
+    round (mlfriends.pyx:1057-1058); device: everything O(N^2 d) / O(N d^2).
+
+    Returns ``(maxd_r, f_r, active, failure)``; ``failure`` is ``None`` or ``(round, exception)``
+    for the first round whose host algebra failed (rounds after it are not evaluated, like the
+    reference's loop).  Rounds with all/none selected are inactive (mlfriends.pyx:1048-1049).
+    """
+    nrounds, N = selected.shape
+    ndim = u.shape[1]
+    active = ~(selected.all(axis=1) | ~selected.any(axis=1))
+    ctrs = np.zeros((nrounds, ndim))
+    invcovs = np.zeros((nrounds, ndim, ndim))
+    failure = None
+    stop = hi
+    for r in range(lo, hi):
+        if not active[r]:
+            continue
+        try:
+            ctr, cov = bounding_ellipsoid(u[selected[r], :], minvol=minvol)
+            invcovs[r] = np.linalg.inv(cov)
+            ctrs[r] = ctr
+        except (np.linalg.LinAlgError, FloatingPointError, AssertionError, Warning) as exc:
+            failure = (r, exc)
+            stop = r
+            break
+    if stop > lo:
+        maxd_r, f_r = _engine().region_bootstrap(unormed, selected, u=u, ctrs=ctrs,
+                                                 invcovs=invcovs, round_lo=lo, round_hi=stop)
+    else:
+        maxd_r, f_r = np.zeros(nrounds), np.zeros(nrounds)
+    return maxd_r, f_r, active, failure
+
+
 class MLFriends(object):
     """MLFriends region (mlfriends.pyx:915-1257): union of equal-radius balls around the live
     points in the whitened space, intersected with a wrapping ellipsoid."""
@@ -501,26 +536,21 @@ class MLFriends(object):
 
         Host: the selection masks (``rng`` order preserved) and each round's d x d
         ``bounding_ellipsoid`` / ``inv``.  Device: all rounds' nearest-neighbour max-min scans
-        and einsum maxima in one launch each.
+        and einsum maxima in one launch each.  With :mod:`ultranest_b200.distributed` enabled
+        the rounds are sharded over the ranks and re-united by ONE allreduce(MAX)
+        (the reference's gather+bcast, integrator.py:395-404).
         """
+        from . import distributed
         N, ndim = self.u.shape
         assert np.isfinite(self.unormed).all(), self.unormed
         selected, state = _draw_rounds(rng, N, nbootstraps)
-        active = ~(selected.all(axis=1) | ~selected.any(axis=1))
-        ctrs = np.zeros((nbootstraps, ndim))
-        invcovs = np.zeros((nbootstraps, ndim, ndim))
-        for r in range(nbootstraps):
-            if not active[r]:
-                continue
-            try:
-                ctr, cov = bounding_ellipsoid(self.u[selected[r], :], minvol=minvol)
-                invcovs[r] = np.linalg.inv(cov)
-            except Exception:
-                _rewind_rounds(rng, state, N, r + 1)
-                raise
-            ctrs[r] = ctr
-        maxd_r, f_r = _engine().region_bootstrap(self.unormed, selected, u=self.u, ctrs=ctrs,
-                                                 invcovs=invcovs)
+        if distributed.world_size() > 1:
+            return distributed.reduce_enlargement(self.u, self.unormed, selected, minvol)
+        maxd_r, f_r, active, failure = _bootstrap_rounds(self.u, self.unormed, selected, 0,
+                                                         nbootstraps, minvol)
+        if failure is not None:
+            _rewind_rounds(rng, state, N, failure[0] + 1)
+            raise failure[1]
         maxd = 0.0
         maxf = 0.0
         for r in range(nbootstraps):
@@ -530,7 +560,7 @@ class MLFriends(object):
             f = f_r[r]
             if not np.isfinite(f) or not f > 0:
                 _rewind_rounds(rng, state, N, r + 1)
-                assert np.isfinite(f), (ctrs[r], self.unormed, f, invcovs[r])
+                assert np.isfinite(f), (self.unormed, f)
                 raise np.linalg.LinAlgError("Distances are not positive")
             maxf = max(maxf, f)
         assert maxd > 0, (maxd, self.u, self.unormed)
