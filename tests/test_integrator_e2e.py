@@ -46,9 +46,14 @@ def swapped_modules():
     names = ("AffineLayer", "LocalAffineLayer", "MLFriends", "RobustEllipsoidRegion",
              "ScalingLayer", "WrappingEllipsoid", "find_nearby")
     saved = {n: getattr(integ, n) for n in names}
+    fns = [fn for cls in vars(integ).values() if isinstance(cls, type)
+           for fn in vars(cls).values() if getattr(fn, "__defaults__", None)]
+    saved_defaults = [(fn, fn.__defaults__) for fn in fns]
     yield integ, refmod
     for n, v in saved.items():
         setattr(integ, n, v)
+    for fn, d in saved_defaults:
+        fn.__defaults__ = d
     sys.modules["ultranest.mlfriends"] = refmod
     sys.modules["ultranest"].mlfriends = refmod
 

@@ -37,8 +37,18 @@ def install(force=False):
         if not force:
             raise RuntimeError("ultranest.integrator is already imported; call "
                                "ultranest_b200.install() first or pass force=True")
+        replaced = {}
         for name in ("AffineLayer", "LocalAffineLayer", "MLFriends", "RobustEllipsoidRegion",
                      "ScalingLayer", "WrappingEllipsoid", "find_nearby"):
             if hasattr(already, name):
+                replaced[id(getattr(already, name))] = getattr(ours, name)
                 setattr(already, name, getattr(ours, name))
+        # default arguments (``run(..., region_class=MLFriends)``) were bound at import time
+        for cls in vars(already).values():
+            if not isinstance(cls, type):
+                continue
+            for fn in vars(cls).values():
+                defaults = getattr(fn, "__defaults__", None)
+                if defaults and any(id(v) in replaced for v in defaults):
+                    fn.__defaults__ = tuple(replaced.get(id(v), v) for v in defaults)
     return ours
