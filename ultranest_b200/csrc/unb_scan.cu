@@ -485,6 +485,9 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
     }
 
     unsigned long long rechecks = 0;
+    unsigned long long pend[TM];   // per slot: bit (g*4+n) = live point of the tile to decide
+#pragma unroll
+    for (int m = 0; m < TM; m++) pend[m] = 0ull;
     bool warp_idle = false;   // a warp with no live slot skips the tile (drain phase)
     for (unsigned tt = 0;; tt++) {
         const int buf = tt & 1;
@@ -513,24 +516,31 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
                         acc[m][3] = fma(a[m][k], b.w, acc[m][3]);
                     }
                 }
-                bool any = false;
+                // record the pairs that pass the filter; they are decided after the tile, all
+                // lanes at once, instead of serialising the warp on every hit
 #pragma unroll
-                for (int m = 0; m < TM; m++)
+                for (int m = 0; m < TM; m++) {
+                    unsigned nib = 0;
 #pragma unroll
-                    for (int n = 0; n < TN; n++) any |= __double2hiint(acc[m][n]) >= thrkey[m];
-                if (any) {
+                    for (int n = 0; n < TN; n++)
+                        nib |= (__double2hiint(acc[m][n]) >= thrkey[m]) ? (1u << n) : 0u;
+                    pend[m] |= (unsigned long long)nib << (g * TN);
+                }
+            }
+            // ---- decide: exact reference arithmetic for the recorded pairs (any order is fine
+            // for a membership test)
 #pragma unroll
-                    for (int m = 0; m < TM; m++) {
-#pragma unroll
-                        for (int n = 0; n < TN; n++) {
-                            if (__double2hiint(acc[m][n]) >= thrkey[m]) {
-                                rechecks++;
-                                const double D = exact_dist_reg<DR>(a[m], Tg + n);
-                                if (D <= A.r2) {
-                                    hit[m] = 1;
-                                    thrkey[m] = INT_MAX;
-                                }
-                            }
+            for (int m = 0; m < TM; m++) {
+                while (__any_sync(FULL, pend[m] != 0ull)) {
+                    if (pend[m] != 0ull) {
+                        const int col = __ffsll((long long)pend[m]) - 1;
+                        pend[m] &= pend[m] - 1ull;
+                        rechecks++;
+                        const double D = exact_dist_reg<DR>(a[m], T + col);
+                        if (D <= A.r2) {
+                            hit[m] = 1;
+                            thrkey[m] = INT_MAX;
+                            pend[m] = 0ull;
                         }
                     }
                 }
