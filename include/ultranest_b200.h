@@ -145,6 +145,11 @@ int unb_region_inside(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
                       int64_t *idx_out);
 int unb_region_inside_dev(unb_ctx *ctx, const double *pts_dev, size_t m, uint8_t *mask_dev,
                           void *stream);
+/* Same pipeline without the ellipsoid stage: transform + neighbour scan of u-space proposals,
+ * i.e. `find_nearby(self.unormed, transformLayer.transform(w), ...) >= 0` of
+ * sample_from_wrapping_ellipsoid (mlfriends.pyx:1155-1158). */
+int unb_region_friends(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
+                       int64_t *idx_out);
 
 /* find_nearby / count_nearby of t-space candidates against the mirrored live block
  * (mlfriends.pyx:1110, 1125, 1157, 1088). */

@@ -69,6 +69,7 @@ def test_gaussian_run_is_identical(swapped_modules):
     assert got["ncall"] == want["ncall"]
     assert got["ncall_region"] == want["ncall_region"]
     assert abs(got["logz"] - want["logz"]) <= 1e-10 * abs(want["logz"])
+    assert got["logz"] == want["logz"], "same host: expected the identical run, bit for bit"
     # and with the likelihood batch call on the device as well
     from ultranest_b200.likelihoods import GaussianLogLike
     got2 = run_once(GaussianLogLike(0.5, SIGMA))

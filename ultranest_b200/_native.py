@@ -65,6 +65,7 @@ SIGNATURES = {
     "unb_region_set_ellipsoid": [_c_vp, _c_vp, _dbl, _sz],
     "unb_region_set_radius": [_dbl],
     "unb_region_inside": [_c_vp, _sz, _c_vp, _c_vp],
+    "unb_region_friends": [_c_vp, _sz, _c_vp, _c_vp],
     "unb_region_inside_dev": [_c_vp, _sz, _c_vp, _c_vp],
     "unb_region_find_nearby": [_c_vp, _sz, _c_vp],
     "unb_region_count_nearby": [_c_vp, _sz, _c_vp],
@@ -311,11 +312,12 @@ class Engine(object):
     def region_set_radius(self, maxradiussq):
         self.call("unb_region_set_radius", float(maxradiussq))
 
-    def region_inside(self, pts, want_index=False):
+    def region_inside(self, pts, want_index=False, use_ellipsoid=True):
         p = as_f64(pts, 2)
         mask = np.empty(len(p), dtype=bool)
         idx = np.empty(len(p), dtype=np.int64) if want_index else None
-        self.call("unb_region_inside", _ptr(p), len(p), _ptr(mask), _ptr(idx))
+        name = "unb_region_inside" if use_ellipsoid else "unb_region_friends"
+        self.call(name, _ptr(p), len(p), _ptr(mask), _ptr(idx))
         return (mask, idx) if want_index else mask
 
     def region_find_nearby(self, tpts):

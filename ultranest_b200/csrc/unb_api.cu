@@ -628,7 +628,7 @@ int region_ready(unb_ctx *ctx, bool need_ellipsoid)
 // enqueue MLFriends.inside (+ optional likelihood) for device-resident rows on lane `ln`
 int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev, size_t m,
                    unsigned char *mask_dev, long long *idx_dev, double *like_dev,
-                   int loglike_kind)
+                   int loglike_kind, bool use_ellipsoid = true)
 {
     RegionState &R = ctx->region;
     const size_t d = R.live.d;
@@ -647,7 +647,7 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     p.pts = pts_dev;
     p.m = (long long)m;
     p.d = (int)d;
-    p.center = (const double *)R.ell_center.p;
+    p.center = use_ellipsoid ? (const double *)R.ell_center.p : nullptr;
     p.invcov = (const double *)R.ell_invcov.p;
     p.r2 = R.enlarge;
     p.mask = mask_dev;
@@ -714,7 +714,7 @@ int upload_lparams(unb_ctx *ctx, int kind, const double *lparams, size_t d, cuda
 
 // chunked, double-buffered host pipeline: H2D(c+1) overlaps kernels(c) and D2H(c)
 int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_t *idx_out,
-                double *like, int loglike_kind)
+                double *like, int loglike_kind, bool use_ellipsoid = true)
 {
     RegionState &R = ctx->region;
     const size_t d = R.live.d;
@@ -751,7 +751,8 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
             UNB_TRY(enqueue_inside(ctx, ln, s, (const double *)ln.cand.p, rows,
                                    (unsigned char *)ln.mask.p,
                                    idx_out ? (long long *)ln.idx.p : nullptr,
-                                   like ? (double *)ln.like.p : nullptr, loglike_kind));
+                                   like ? (double *)ln.like.p : nullptr, loglike_kind,
+                                   use_ellipsoid));
             ln.pend_rows = 0;
             if (mask_pinned) {
                 UNB_TRY(d2h(ctx, mask + off, ln.mask.p, rows, s));
@@ -807,6 +808,16 @@ extern "C" int unb_region_inside(unb_ctx *ctx, const double *pts, size_t m, uint
     if (m == 0) return UNB_OK;
     if (!pts || !mask) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     return inside_host(ctx, pts, m, mask, idx_out, nullptr, UNB_LOGLIKE_NONE);
+}
+
+extern "C" int unb_region_friends(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
+                                  int64_t *idx_out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(region_ready(ctx, true));
+    if (m == 0) return UNB_OK;
+    if (!pts || !mask) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    return inside_host(ctx, pts, m, mask, idx_out, nullptr, UNB_LOGLIKE_NONE, false);
 }
 
 extern "C" int unb_region_inside_loglike(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,

@@ -289,23 +289,24 @@ class ScalingLayer(object):
 
     # -- device parameters ---------------------------------------------------------------
     def _device_params(self, ndim):
-        """(kind, shift[d], scale[d]) for the kernels."""
+        """(kind, shift[d], scale[d]) for the fused device pipelines."""
         mean = np.ascontiguousarray(np.broadcast_to(np.ravel(self.mean), (ndim,)), dtype=float)
         std = np.ascontiguousarray(np.broadcast_to(np.ravel(self.std), (ndim,)), dtype=float)
         return _native.LAYER_SCALING, mean, std
 
     def transform(self, u):
-        """Cube space -> whitened space: ``(w - mean) / std``, elementwise on the device."""
-        u = np.asarray(u, dtype=float)
+        """Cube space -> whitened space, ``(w - mean) / std`` (mlfriends.pyx:605-611).
+
+        This method carries VALUES into the run (``region.unormed``, the t-space bounding box),
+        so it is the reference's own NumPy expression; bulk proposals are transformed on the
+        device inside the fused pipelines (``MLFriends.inside`` ...), where only decisions depend
+        on it.  (``unb_transform_scaling`` gives the same bits.)"""
         w = self.wrap(u) if self.has_wraps else u
-        kind, shift, mat = self._device_params(u.shape[-1])
-        return _engine().transform(kind, False, w, shift, mat).reshape(u.shape)
+        return ((w - self.mean) / self.std).reshape(u.shape)
 
     def untransform(self, ww):
-        """Whitened space -> cube space: ``ww * std + mean`` (then unwrap)."""
-        ww = np.asarray(ww, dtype=float)
-        kind, shift, mat = self._device_params(ww.shape[-1])
-        w = _engine().transform(kind, True, ww, shift, mat)
+        """Whitened space -> cube space (mlfriends.pyx:613-620)."""
+        w = (ww * self.std) + self.mean
         if self.has_wraps:
             return self.unwrap(w).reshape(ww.shape)
         return w.reshape(ww.shape)
@@ -315,9 +316,11 @@ class AffineLayer(ScalingLayer):
     """Affine whitening learned from the (cluster-centred) sample covariance
     (mlfriends.pyx:623-752).
 
-    ``transform`` is ``(w - ctr) . T`` like the reference's ``np.dot``; the summation order is
-    the library's defined one (k ascending, fused multiply-add), identical for a single row and
-    for a batch, so a live point transformed alone equals its row in ``region.unormed``.
+    ``transform`` / ``untransform`` carry values into the run (``region.unormed``, bounding box,
+    returned samples) and are the reference's own ``np.dot`` expressions, so a seeded run
+    reproduces the reference's numbers exactly.  Bulk proposals are transformed on the device
+    inside the fused pipelines with the library's defined order (k ascending, fused multiply-add;
+    DESIGN.md 4.4), where only accept/reject decisions depend on it.
     """
 
     _kind = _native.LAYER_AFFINE
@@ -364,21 +367,13 @@ class AffineLayer(ScalingLayer):
                 np.ascontiguousarray(self.T, dtype=float))
 
     def transform(self, u):
-        u = np.asarray(u, dtype=float)
+        """Cube space -> whitened space, ``np.dot(w - ctr, T)`` (mlfriends.pyx:737-743)."""
         w = self.wrap(u) if self.has_wraps else u
-        if not self._is_learned():   # constructor defaults (scalars): nothing to whiten yet
-            return np.dot(w - self.ctr, self.T)
-        kind, shift, mat = self._device_params(u.shape[-1])
-        return _engine().transform(kind, False, w, shift, mat).reshape(u.shape)
+        return np.dot(w - self.ctr, self.T)
 
     def untransform(self, ww):
-        ww = np.asarray(ww, dtype=float)
-        if not self._is_learned():
-            w = np.dot(ww, self.invT) + self.ctr
-        else:
-            w = _engine().transform(_native.LAYER_AFFINE, True, ww,
-                                    np.ascontiguousarray(self.ctr, dtype=float),
-                                    np.ascontiguousarray(self.invT, dtype=float))
+        """Whitened space -> cube space (mlfriends.pyx:745-752)."""
+        w = np.dot(ww, self.invT) + self.ctr
         if self.has_wraps:
             return self.unwrap(w).reshape(ww.shape)
         return w.reshape(ww.shape)
@@ -583,12 +578,17 @@ class MLFriends(object):
         return eng
 
     def _fused_ok(self):
+        """May proposals be transformed on the device?  Not with circular dimensions (host wrap),
+        not before the layer is learned, and not when the radius is so small that the ulp-level
+        difference between the device transform and ``np.dot`` could matter (a live point must
+        stay inside its own ball even for ``maxradiussq = 1e-90``, test_regionsampling.py:46-48)."""
         layer = self.transformLayer
         if layer.has_wraps:
             return False
         if isinstance(layer, AffineLayer) and not layer._is_learned():
             return False
-        return True
+        scale2 = max(float(np.max(np.abs(self.bbox_lo))), float(np.max(np.abs(self.bbox_hi))), 1e-300)**2
+        return self.maxradiussq > 1e-18 * scale2 * self.u.shape[1]
 
     # -- sampling (host RNG in the reference's order, device filters) ----------------------
     def sample_from_points(self, nsamples=100):
@@ -634,8 +634,11 @@ class MLFriends(object):
         u = z * self.enlarge**0.5 * np.random.uniform(size=(nsamples, 1))**(1. / ndim)
         w = self.ellipsoid_center + np.dot(u, self.ellipsoid_axes_T)
         wmask = np.logical_and(w > 0, w < 1).all(axis=1)
-        v = self.transformLayer.transform(w[wmask, :])
-        vmask = self._bind(need_ellipsoid=False).region_find_nearby(v) >= 0
+        if self._fused_ok():     # transform + neighbour scan in one device pipeline
+            vmask = self._bind().region_inside(w[wmask, :], use_ellipsoid=False)
+        else:
+            v = self.transformLayer.transform(w[wmask, :])
+            vmask = self._bind(need_ellipsoid=False).region_find_nearby(v) >= 0
         return w[wmask, :][vmask, :]
 
     def sample(self, nsamples=100):
