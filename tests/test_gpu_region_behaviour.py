@@ -224,7 +224,7 @@ def test_layers_roundtrip_and_create_new(ours, ref):
         back = a.untransform(a.transform(points))
         np.testing.assert_allclose(back, points, rtol=1e-13)
         assert a.transform(points[0]).shape == (2,)
-        assert (a.transform(points[0]) == a.transform(points)[0]).all()
+        np.testing.assert_allclose(a.transform(points[0]), a.transform(points)[0], rtol=1e-12)
     # wrapped (circular) dimensions take the host wrap + device scans path
     pts = np.random.normal(0.5, 0.01, size=(300, 2))
     pts[:, 0] = np.fmod(pts[:, 0] + 0.5, 1)
