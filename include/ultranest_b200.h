@@ -50,6 +50,8 @@ extern "C" {
                                         in the last scan call (diagnostic)                */
 #define UNB_STAT_H2D_BYTES 3
 #define UNB_STAT_D2H_BYTES 4
+#define UNB_STAT_TILE_VISITS 5       /* warp x tile filter passes of the last
+                                        unb_region_find_nearby_dev(mask-only) call (diagnostic) */
 
 /* transform-layer kinds for unb_region_set_layer */
 #define UNB_LAYER_IDENTITY 0
@@ -72,6 +74,9 @@ const char *unb_last_error(const unb_ctx *ctx);
 int unb_ctx_set_option(unb_ctx *ctx, int option, int64_t value);
 int unb_ctx_get_stat(unb_ctx *ctx, int stat, int64_t *value);
 int unb_ctx_synchronize(unb_ctx *ctx);
+/* measured fp64 FMA rate of the device (lane-FMAs per second): the compute-roofline denominator
+ * bench.py reports next to the HBM one */
+int unb_fp64_peak(unb_ctx *ctx, double *dfma_per_s);
 
 /* --------------------------------------------- stateless scans (host buffers) */
 

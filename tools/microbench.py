@@ -78,6 +78,14 @@ def main():
                             ref_pairdims_per_s_any=visited.sum() * d / ms_any * 1e3,
                             fullscan_pairdims_per_s_find=(4000.0 * M * d / ms_find * 1e3) if regime == "R" else None,
                             hbm_gbs_any=(M * (8 * d + 1) + 4000 * d * 8) / ms_any / 1e6))
+        if d == 20:   # launch-size sweep of the membership kernel: slope = steady state, intercept = drain
+            t_all = torch.from_numpy(np.ascontiguousarray(region.transformLayer.transform(cand))).cuda()
+            mask = torch.empty(M, dtype=torch.uint8, device="cuda")
+            for msub in (4096, 65536, 262144, M):
+                ms = timed(lambda: eng.call("unb_region_find_nearby_dev", t_all.data_ptr(), msub,
+                                            None, mask.data_ptr(), sh), stream)
+                out.append(dict(case="any_size_sweep", d=d, m=msub, ms=ms,
+                                tile_units=eng.stat(_native.STAT_TILE_VISITS)))
         # fused inside (u-space proposals, mask only)
         p_dev = torch.from_numpy(cand).cuda()
         mask = torch.empty(M, dtype=torch.uint8, device="cuda")

@@ -25,6 +25,7 @@ STAT_KERNEL_LAUNCHES = 1
 STAT_RECHECKS = 2
 STAT_H2D_BYTES = 3
 STAT_D2H_BYTES = 4
+STAT_TILE_VISITS = 5
 
 LAYER_IDENTITY = 0
 LAYER_SCALING = 1
@@ -50,6 +51,7 @@ SIGNATURES = {
     "unb_ctx_set_option": [_int, _i64],
     "unb_ctx_get_stat": [_int, _c_ip],
     "unb_ctx_synchronize": [],
+    "unb_fp64_peak": [_c_dp],
     "unb_find_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_count_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_subtract_nearby": [_c_vp, _sz, _sz, _dbl, _c_vp],
@@ -198,6 +200,12 @@ class Engine(object):
 
     def synchronize(self):
         self.call("unb_ctx_synchronize")
+
+    def fp64_peak(self):
+        """Measured fp64 FMA rate of this device (lane-FMAs per second)."""
+        v = _dbl(0.0)
+        self.call("unb_fp64_peak", ctypes.byref(v))
+        return float(v.value)
 
     # -- stateless scans ---------------------------------------------------------------
     def find_nearby(self, apts, bpts, radiussq, out=None):

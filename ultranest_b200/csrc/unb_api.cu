@@ -124,8 +124,8 @@ int check_ctx(unb_ctx *ctx)
 
 int stat_reset(unb_ctx *ctx, cudaStream_t s)
 {
-    UNB_TRY(unb_reserve(ctx, ctx->stat, sizeof(unsigned long long)));
-    UNB_CUDA(ctx, cudaMemsetAsync(ctx->stat.p, 0, sizeof(unsigned long long), s));
+    UNB_TRY(unb_reserve(ctx, ctx->stat, 2 * sizeof(unsigned long long)));   // rechecks, tile visits
+    UNB_CUDA(ctx, cudaMemsetAsync(ctx->stat.p, 0, 2 * sizeof(unsigned long long), s));
     return UNB_OK;
 }
 int stat_fetch(unb_ctx *ctx, cudaStream_t s)
@@ -296,8 +296,46 @@ extern "C" int unb_ctx_get_stat(unb_ctx *ctx, int stat, int64_t *value)
     case UNB_STAT_RECHECKS: *value = ctx->last_rechecks; return UNB_OK;
     case UNB_STAT_H2D_BYTES: *value = ctx->h2d_bytes; return UNB_OK;
     case UNB_STAT_D2H_BYTES: *value = ctx->d2h_bytes; return UNB_OK;
+    case UNB_STAT_TILE_VISITS: {
+        // refresh from the device counter (written by the any-neighbour kernel)
+        unsigned long long v[2] = {0, 0};
+        if (ctx->stat.p) {
+            UNB_CUDA(ctx, cudaDeviceSynchronize());
+            UNB_CUDA(ctx, cudaMemcpy(v, ctx->stat.p, sizeof(v), cudaMemcpyDeviceToHost));
+        }
+        *value = (long long)v[1];
+        return UNB_OK;
+    }
     default: return unb_fail(ctx, UNB_ERR_ARG, "unknown stat %d", stat);
     }
+}
+
+// measured DFMA issue rate of this device (warp-wide fused multiply-adds x 32 lanes per second)
+extern "C" int unb_fp64_peak(unb_ctx *ctx, double *dfma_per_s)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!dfma_per_s) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    cudaStream_t s = S0(ctx);
+    UNB_TRY(unb_reserve(ctx, ctx->aux0, 64));
+    const int blocks = ctx->sm_count * 8, iters = 20000;
+    cudaEvent_t e0, e1;
+    UNB_CUDA(ctx, cudaEventCreate(&e0));
+    UNB_CUDA(ctx, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        UNB_CUDA(ctx, cudaEventRecord(e0, s));
+        UNB_TRY(unb_launch_fp64_peak(ctx, (double *)ctx->aux0.p, blocks, iters, s));
+        UNB_CUDA(ctx, cudaEventRecord(e1, s));
+        UNB_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        UNB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *dfma_per_s = best;
+    return UNB_OK;
 }
 
 extern "C" int unb_ctx_synchronize(unb_ctx *ctx)
@@ -887,6 +925,9 @@ extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, 
     Lane &ln = ctx->lane[0];
     UNB_TRY(unb_reserve(ctx, ln.counter, 2 * sizeof(int)));
     UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 2 * sizeof(int), s));
+    UNB_TRY(stat_reset(ctx, s));
+    a.stat_rechecks = (unsigned long long *)ctx->stat.p;
+    a.stat_tiles = (unsigned long long *)ctx->stat.p + 1;
     return unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s);
 }
 

@@ -110,6 +110,7 @@ struct ScanArgs {
     double *out_like;         // any-kernel: rows without a neighbour get -inf (nullable)
     unsigned long long *out_round_max;   // MIN: per-round max over candidates (ordered bits)
     unsigned long long *stat_rechecks;   // diagnostic counter (nullable)
+    unsigned long long *stat_tiles;      // diagnostic: warp-tiles filtered (nullable)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -153,6 +154,7 @@ struct unb_ctx {
     long long launches = 0;
     long long h2d_bytes = 0, d2h_bytes = 0;
     long long last_rechecks = 0;
+    long long last_tile_visits = 0;
     int exact_only = 0;
     long long chunk_rows = 0;
 
@@ -219,6 +221,7 @@ int unb_launch_enlargement_f(unb_ctx *ctx, const double *u, int d, const int *it
 int unb_launch_pairdist(unb_ctx *ctx, const double *pts, const long long *ids, int n, int d,
                         double *partial_sum, long long *partial_cnt, cudaStream_t s);
 size_t unb_max_rowwise_d();
+int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------
 // device helpers

@@ -385,7 +385,32 @@ __global__ void k_pairdist(const double *__restrict__ pts, const long long *__re
     partial_cnt[j] = cnt;
 }
 
+// ---------------------------------------------------------------------------------------
+// fp64 pipe peak probe: 8 independent DFMA chains per thread, no memory traffic.  Gives the
+// measured denominator for the compute roofline of the scan kernels on THIS device and clock.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) out[0] = r;   // keeps the chains alive
+}
+
 }  // namespace
+
+int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, cudaStream_t s)
+{
+    k_fp64_peak<<<blocks, 256, 0, s>>>(scratch, iters, 1.0);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
 
 size_t unb_max_rowwise_d() { return ROW_SMEM_BUDGET / sizeof(double) / 32 - 1; }
 

@@ -392,18 +392,62 @@ __global__ void __launch_bounds__(SCAN_THREADS, reg_min_blocks(DR, TM)) k_scan_r
 // still searching (the ordered kernel above pays the warp-maximum of the first-hit positions).
 // Decisions are still made by the exact reference arithmetic, so the mask is bit-identical.
 // ---------------------------------------------------------------------------------------
+// filter pass of one shared-memory tile for the first TMA slots of every thread: records the
+// pairs that pass the filter in pend[m] (bit g*4+n = live point of the tile)
+template <int DR, int TM, int TMA>
+__device__ __forceinline__ void tile_filter(const double (&a)[TM][DR], const int (&thrkey)[TM],
+                                            unsigned long long (&pend)[TM], const double *T)
+{
+#pragma unroll 1
+    for (int g = 0; g < REG_TILE_N / TN; g++) {
+        const double *Tg = T + g * TN;
+        double acc[TMA][TN];
+        {
+            const double4 h = *reinterpret_cast<const double4 *>(Tg + DR * REG_TILE_N);
+#pragma unroll
+            for (int m = 0; m < TMA; m++) {
+                acc[m][0] = h.x; acc[m][1] = h.y; acc[m][2] = h.z; acc[m][3] = h.w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DR; k++) {
+            const double4 b = *reinterpret_cast<const double4 *>(Tg + k * REG_TILE_N);
+#pragma unroll
+            for (int m = 0; m < TMA; m++) {
+                acc[m][0] = fma(a[m][k], b.x, acc[m][0]);
+                acc[m][1] = fma(a[m][k], b.y, acc[m][1]);
+                acc[m][2] = fma(a[m][k], b.z, acc[m][2]);
+                acc[m][3] = fma(a[m][k], b.w, acc[m][3]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < TMA; m++) {
+            unsigned nib = 0;
+#pragma unroll
+            for (int n = 0; n < TN; n++)
+                nib |= (__double2hiint(acc[m][n]) >= thrkey[m]) ? (1u << n) : 0u;
+            pend[m] |= (unsigned long long)nib << (g * TN);
+        }
+    }
+}
+
+constexpr int ANY_STAGE_SLOTS = SCAN_THREADS;   // capacity of the compaction staging area
+
 template <int DR, int TM>
 __global__ void __launch_bounds__(SCAN_THREADS, reg_min_blocks(DR, TM))
 k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    int *s_info = reinterpret_cast<int *>(smem_raw + 64);           // per warp: live slots | exhausted<<16
     constexpr int TILE_DOUBLES = (DR + 1) * REG_TILE_N;
     constexpr uint32_t TILE_BYTES = TILE_DOUBLES * sizeof(double);
     double *tbuf = reinterpret_cast<double *>(smem_raw + 128);
+    double *stage = tbuf + 2 * TILE_DOUBLES;                        // [DR+2][ANY_STAGE_SLOTS]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const int warp = tid >> 5;
     const double *tiles = A.tiles;
     const int ntiles = (A.n_live + REG_TILE_N - 1) / REG_TILE_N;
     const int n_items = A.n_items_dev ? *A.n_items_dev : (int)A.n_items;
@@ -412,9 +456,10 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
 
     double a[TM][DR];
     int row[TM], orow[TM], rem[TM], thrkey[TM], hit[TM];
+    unsigned long long pend[TM];   // per slot: bit (g*4+n) = live point of the tile to decide
 #pragma unroll
     for (int m = 0; m < TM; m++) {
-        row[m] = -1; orow[m] = -1; rem[m] = 0; thrkey[m] = INT_MAX; hit[m] = 0;
+        row[m] = -1; orow[m] = -1; rem[m] = 0; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull;
 #pragma unroll
         for (int k = 0; k < DR; k++) a[m][k] = 0.0;
     }
@@ -485,50 +530,24 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
     }
 
     unsigned long long rechecks = 0;
-    unsigned long long pend[TM];   // per slot: bit (g*4+n) = live point of the tile to decide
-#pragma unroll
-    for (int m = 0; m < TM; m++) pend[m] = 0ull;
+    unsigned int tile_units = 0;
     bool warp_idle = false;   // a warp with no live slot skips the tile (drain phase)
+    bool single = (TM == 1);  // block-uniform: every live slot sits in m = 0 (after a compaction)
+    int cap = SCAN_THREADS * TM;   // slots the block is spread over
     for (unsigned tt = 0;; tt++) {
         const int buf = tt & 1;
         mbar_wait(&bars[buf], (tt >> 1) & 1);
         const double *T = tbuf + buf * TILE_DOUBLES;
         if (!warp_idle) {
-#pragma unroll 1
-            for (int g = 0; g < REG_TILE_N / TN; g++) {
-                const double *Tg = T + g * TN;
-                double acc[TM][TN];
-                {
-                    const double4 h = *reinterpret_cast<const double4 *>(Tg + DR * REG_TILE_N);
-#pragma unroll
-                    for (int m = 0; m < TM; m++) {
-                        acc[m][0] = h.x; acc[m][1] = h.y; acc[m][2] = h.z; acc[m][3] = h.w;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < DR; k++) {
-                    const double4 b = *reinterpret_cast<const double4 *>(Tg + k * REG_TILE_N);
-#pragma unroll
-                    for (int m = 0; m < TM; m++) {
-                        acc[m][0] = fma(a[m][k], b.x, acc[m][0]);
-                        acc[m][1] = fma(a[m][k], b.y, acc[m][1]);
-                        acc[m][2] = fma(a[m][k], b.z, acc[m][2]);
-                        acc[m][3] = fma(a[m][k], b.w, acc[m][3]);
-                    }
-                }
-                // record the pairs that pass the filter; they are decided after the tile, all
-                // lanes at once, instead of serialising the warp on every hit
-#pragma unroll
-                for (int m = 0; m < TM; m++) {
-                    unsigned nib = 0;
-#pragma unroll
-                    for (int n = 0; n < TN; n++)
-                        nib |= (__double2hiint(acc[m][n]) >= thrkey[m]) ? (1u << n) : 0u;
-                    pend[m] |= (unsigned long long)nib << (g * TN);
-                }
+            if (single) {
+                tile_units += 1;
+                tile_filter<DR, TM, 1>(a, thrkey, pend, T);
+            } else {
+                tile_units += TM;
+                tile_filter<DR, TM, TM>(a, thrkey, pend, T);
             }
-            // ---- decide: exact reference arithmetic for the recorded pairs (any order is fine
-            // for a membership test)
+            // ---- decide: exact reference arithmetic for the recorded pairs, all lanes at once
+            // (any order is fine for a membership test)
 #pragma unroll
             for (int m = 0; m < TM; m++) {
                 while (__any_sync(FULL, pend[m] != 0ull)) {
@@ -549,14 +568,30 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
             for (int m = 0; m < TM; m++) rem[m]--;
             refill();
         }
-        bool idle = true;
+        // ---- block bookkeeping: live slots per warp, queue state
+        int mine = 0;
 #pragma unroll
-        for (int m = 0; m < TM; m++) idle &= row[m] < 0;
-        warp_idle = __all_sync(FULL, idle);
-        const bool all_idle = __syncthreads_and(idle);
-        if (all_idle) {
-            // tile tt+1 is always in flight
-            mbar_wait(&bars[(tt + 1) & 1], ((tt + 1) >> 1) & 1);
+        for (int m = 0; m < TM; m++) mine += row[m] >= 0;
+        int incl = mine;   // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int *info = s_info + (tt & 1) * (SCAN_THREADS / 32);   // double-buffered across iterations
+        if (lane == 31) info[warp] = incl | ((exhausted ? 1 : 0) << 16);
+        __syncthreads();   // also: every thread is done with tile `buf`
+        int total = 0, warp_off = 0;
+        bool all_exh = true;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; w++) {
+            const int v = info[w];
+            if (w < warp) warp_off += v & 0xffff;
+            total += v & 0xffff;
+            all_exh &= (v >> 16) != 0;
+        }
+        if (total == 0) {
+            mbar_wait(&bars[(tt + 1) & 1], ((tt + 1) >> 1) & 1);   // tile tt+1 is always in flight
             break;
         }
         if (tid == 0) {
@@ -565,11 +600,46 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
                          tiles + (size_t)((tt + 2) % (unsigned)ntiles) * TILE_DOUBLES, TILE_BYTES,
                          &bars[buf]);
         }
+        // ---- drain: once the queue is empty, pack the surviving slots into as few warps as
+        // possible (slot m = 0 of threads 0..total-1), so the tail costs lanes, not warps
+        if (all_exh && total <= cap / 2 && total <= ANY_STAGE_SLOTS) {
+            int j = warp_off + incl - mine;
+#pragma unroll
+            for (int m = 0; m < TM; m++) {
+                if (row[m] >= 0) {
+#pragma unroll
+                    for (int k = 0; k < DR; k++) stage[k * ANY_STAGE_SLOTS + j] = a[m][k];
+                    stage[DR * ANY_STAGE_SLOTS + j] =
+                        __hiloint2double(row[m], orow[m]);
+                    stage[(DR + 1) * ANY_STAGE_SLOTS + j] =
+                        __hiloint2double(rem[m], thrkey[m]);
+                    j++;
+                }
+                row[m] = -1; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull;
+            }
+            __syncthreads();
+            if (tid < total) {
+#pragma unroll
+                for (int k = 0; k < DR; k++) a[0][k] = stage[k * ANY_STAGE_SLOTS + tid];
+                const double p0 = stage[DR * ANY_STAGE_SLOTS + tid];
+                const double p1 = stage[(DR + 1) * ANY_STAGE_SLOTS + tid];
+                row[0] = __double2hiint(p0); orow[0] = __double2loint(p0);
+                rem[0] = __double2hiint(p1); thrkey[0] = __double2loint(p1);
+            }
+            __syncthreads();   // the staging area may be reused by the next compaction
+            single = true;
+            cap = (total + 31) / 32 * 32;
+        }
+        bool idle = true;
+#pragma unroll
+        for (int m = 0; m < TM; m++) idle &= row[m] < 0;
+        warp_idle = __all_sync(FULL, idle);
     }
     if (A.stat_rechecks) {
         for (int o = 16; o > 0; o >>= 1) rechecks += __shfl_xor_sync(FULL, rechecks, o);
         if (lane == 0 && rechecks) atomicAdd(A.stat_rechecks, rechecks);
     }
+    if (A.stat_tiles && lane == 0) atomicAdd(A.stat_tiles, (unsigned long long)tile_units);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -880,7 +950,8 @@ int launch_mode(unb_ctx *ctx, const ScanArgs &a, int rounds, long long max_items
 template <int DR, int TM>
 int launch_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
 {
-    const size_t smem = 128 + 2 * (size_t)(DR + 1) * REG_TILE_N * sizeof(double);
+    const size_t smem = 128 + (2 * (size_t)(DR + 1) * REG_TILE_N +
+                               (size_t)(DR + 2) * ANY_STAGE_SLOTS) * sizeof(double);
     UNB_TRY(set_smem(ctx, k_inside_any<DR, TM>, smem));
     int per_sm = 0;
     UNB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inside_any<DR, TM>,
