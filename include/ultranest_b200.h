@@ -160,6 +160,8 @@ int unb_region_friends(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
  * (mlfriends.pyx:1110, 1125, 1157, 1088). */
 int unb_region_find_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby);
 int unb_region_count_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby);
+/* `find_nearby(self.unormed, tpts, ...) >= 0` without the index (any-neighbour kernel) */
+int unb_region_has_neighbour(unb_ctx *ctx, const double *tpts, size_t m, uint8_t *mask);
 /* device-pointer variant of the scan alone (nnearby_dev or mask_dev may be NULL) */
 int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, size_t m,
                                int64_t *nnearby_dev, uint8_t *mask_dev, void *stream);

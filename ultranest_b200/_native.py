@@ -71,6 +71,7 @@ SIGNATURES = {
     "unb_region_inside_dev": [_c_vp, _sz, _c_vp, _c_vp],
     "unb_region_find_nearby": [_c_vp, _sz, _c_vp],
     "unb_region_count_nearby": [_c_vp, _sz, _c_vp],
+    "unb_region_has_neighbour": [_c_vp, _sz, _c_vp],
     "unb_region_find_nearby_dev": [_c_vp, _sz, _c_vp, _c_vp, _c_vp],
     "unb_region_bootstrap": [_c_vp, _c_vp, _sz, _sz, _c_vp, _sz, _sz, _sz, _c_vp, _c_vp,
                              _c_vp, _c_vp],
@@ -333,6 +334,13 @@ class Engine(object):
         out = np.empty(len(p), dtype=np.int64)
         self.call("unb_region_find_nearby", _ptr(p), len(p), _ptr(out))
         return out
+
+    def region_has_neighbour(self, tpts):
+        """``find_nearby(unormed, tpts, r2) >= 0`` as a mask (no index needed)."""
+        p = as_f64(tpts, 2)
+        mask = np.empty(len(p), dtype=bool)
+        self.call("unb_region_has_neighbour", _ptr(p), len(p), _ptr(mask))
+        return mask
 
     def region_count_nearby(self, tpts):
         p = as_f64(tpts, 2)

@@ -617,7 +617,7 @@ class MLFriends(object):
         N, ndim = self.u.shape
         r = self.maxradiussq**0.5
         v = np.random.uniform(self.bbox_lo - r, self.bbox_hi + r, size=(nsamples, ndim))
-        vmask = self._bind(need_ellipsoid=False).region_find_nearby(v) >= 0
+        vmask = self._bind(need_ellipsoid=False).region_has_neighbour(v)
         w = self.transformLayer.untransform(v[vmask, :])
         wmask = np.logical_and(w > 0, w < 1).all(axis=1)
         wmask[wmask] = self.inside_ellipsoid(w[wmask])
@@ -638,7 +638,7 @@ class MLFriends(object):
             vmask = self._bind().region_inside(w[wmask, :], use_ellipsoid=False)
         else:
             v = self.transformLayer.transform(w[wmask, :])
-            vmask = self._bind(need_ellipsoid=False).region_find_nearby(v) >= 0
+            vmask = self._bind(need_ellipsoid=False).region_has_neighbour(v)
         return w[wmask, :][vmask, :]
 
     def sample(self, nsamples=100):
@@ -662,7 +662,7 @@ class MLFriends(object):
         mask = self.inside_ellipsoid(pts)
         if mask.any():
             bpts = self.transformLayer.transform(pts[mask, :])
-            mask[mask] = self._bind(need_ellipsoid=False).region_find_nearby(bpts) >= 0
+            mask[mask] = self._bind(need_ellipsoid=False).region_has_neighbour(bpts)
         return mask
 
     def inside_and_loglike(self, pts, loglike):
