@@ -86,6 +86,11 @@ int unb_fp64_peak(unb_ctx *ctx, double *dfma_per_s);
 int unb_find_nearby(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
                     size_t nb, size_t ndim, double radiussq, int64_t *nnearby);
 
+/* `find_nearby(...) >= 0` as a mask, without the index: the absorption test of _update_clusters
+ * (mlfriends.pyx:304-307).  Uses the any-neighbour kernel. */
+int unb_has_neighbour(unb_ctx *ctx, const double *apts, size_t na, const double *bpts, size_t nb,
+                      size_t ndim, double radiussq, uint8_t *mask);
+
 /* replaces count_nearby (cdef), mlfriends.pyx:31-68: number of i within radiussq. */
 int unb_count_nearby(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
                      size_t nb, size_t ndim, double radiussq, int64_t *nnearby);

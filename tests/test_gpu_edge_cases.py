@@ -47,6 +47,7 @@ def test_every_dimension_family(eng, d):
     r2 = float(np.median(dist))
     assert (eng.find_nearby(a, b, r2) == cport.find_nearby(a, b, r2)).all()
     assert (eng.count_nearby(a, b, r2) == cport.count_nearby(a, b, r2)).all()
+    assert (eng.has_neighbour(a, b, r2) == (cport.find_nearby(a, b, r2) >= 0)).all()
     assert eng.compute_maxradiussq(a, b) == cport.maxradiussq(a, b)
     if d <= 260:
         assert (eng.subtract_nearby(a, r2) == cport.subtract_nearby(a, r2)).all()

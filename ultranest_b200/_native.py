@@ -54,6 +54,7 @@ SIGNATURES = {
     "unb_fp64_peak": [_c_dp],
     "unb_find_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_count_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
+    "unb_has_neighbour": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_subtract_nearby": [_c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_compute_maxradiussq": [_c_vp, _sz, _c_vp, _sz, _sz, _c_dp],
     "unb_mean_pair_distance": [_c_vp, _c_vp, _sz, _sz, _c_dp],
@@ -221,6 +222,17 @@ class Engine(object):
             out[:len(b)] = res
             return out
         return res
+
+    def has_neighbour(self, apts, bpts, radiussq):
+        """``find_nearby(apts, bpts, radiussq) >= 0`` as a boolean mask."""
+        a = as_f64(apts, 2)
+        b = as_f64(bpts, 2)
+        if a.shape[1] != b.shape[1]:
+            raise ValueError("dimensionality mismatch: %s vs %s" % (a.shape, b.shape))
+        mask = np.empty(len(b), dtype=bool)
+        self.call("unb_has_neighbour", _ptr(a), len(a), _ptr(b), len(b), b.shape[1],
+                  float(radiussq), _ptr(mask))
+        return mask
 
     def count_nearby(self, apts, bpts, radiussq, out=None):
         a = as_f64(apts, 2)

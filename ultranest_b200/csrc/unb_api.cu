@@ -905,6 +905,50 @@ extern "C" int unb_region_find_nearby(unb_ctx *ctx, const double *tpts, size_t m
                      (long long *)nnearby, nullptr, nullptr);
 }
 
+namespace {
+// mask-only scan of host candidates against a built live block (any-neighbour kernel)
+int has_neighbour_host(unb_ctx *ctx, LiveTiles &L, const double *tpts, size_t m, double r2,
+                       uint8_t *mask)
+{
+    Lane &ln = ctx->lane[0];
+    cudaStream_t s = ln.stream;
+    const size_t d = L.d;
+    UNB_TRY(unb_live_set_h(ctx, L, HMODE_THRESH, r2, s));
+    UNB_TRY(unb_reserve(ctx, ln.cand, m * d * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ln.mask, m));
+    UNB_TRY(unb_reserve(ctx, ln.counter, 2 * sizeof(int)));
+    UNB_TRY(h2d(ctx, ln.cand.p, tpts, m * d * sizeof(double), s));
+    UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 2 * sizeof(int), s));
+    UNB_TRY(stat_reset(ctx, s));
+    ScanArgs a = scan_args_for(L);
+    a.cand = (const double *)ln.cand.p;
+    a.n_items = (long long)m;
+    a.r2 = r2;
+    a.out_mask = (unsigned char *)ln.mask.p;
+    a.stat_rechecks = (unsigned long long *)ctx->stat.p;
+    UNB_TRY(unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s));
+    UNB_TRY(d2h(ctx, mask, ln.mask.p, m, s));
+    return stat_fetch(ctx, s);
+}
+}  // namespace
+
+// `find_nearby(apts, bpts, r2, out); out >= 0` without the index (the growth test of
+// _update_clusters, mlfriends.pyx:304-307)
+extern "C" int unb_has_neighbour(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
+                                 size_t nb, size_t ndim, double radiussq, uint8_t *mask)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, na > nb ? na : nb, ndim));
+    if (nb == 0) return UNB_OK;
+    if (!bpts || !mask || (na && !apts)) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (na == 0) {
+        memset(mask, 0, nb);
+        return UNB_OK;
+    }
+    UNB_TRY(live_from_host(ctx, ctx->scratch_live, apts, na, ndim, S0(ctx)));
+    return has_neighbour_host(ctx, ctx->scratch_live, bpts, nb, radiussq, mask);
+}
+
 // mask-only variant of unb_region_find_nearby (what `find_nearby(...) >= 0` callers need): runs
 // the any-neighbour kernel instead of the ordered first-index scan
 extern "C" int unb_region_has_neighbour(unb_ctx *ctx, const double *tpts, size_t m, uint8_t *mask)
@@ -913,25 +957,7 @@ extern "C" int unb_region_has_neighbour(unb_ctx *ctx, const double *tpts, size_t
     UNB_TRY(region_ready(ctx, false));
     if (m == 0) return UNB_OK;
     if (!tpts || !mask) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
-    Lane &ln = ctx->lane[0];
-    cudaStream_t s = ln.stream;
-    const size_t d = ctx->region.live.d;
-    UNB_TRY(unb_live_set_h(ctx, ctx->region.live, HMODE_THRESH, ctx->region.r2, s));
-    UNB_TRY(unb_reserve(ctx, ln.cand, m * d * sizeof(double)));
-    UNB_TRY(unb_reserve(ctx, ln.mask, m));
-    UNB_TRY(unb_reserve(ctx, ln.counter, 2 * sizeof(int)));
-    UNB_TRY(h2d(ctx, ln.cand.p, tpts, m * d * sizeof(double), s));
-    UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 2 * sizeof(int), s));
-    UNB_TRY(stat_reset(ctx, s));
-    ScanArgs a = scan_args_for(ctx->region.live);
-    a.cand = (const double *)ln.cand.p;
-    a.n_items = (long long)m;
-    a.r2 = ctx->region.r2;
-    a.out_mask = (unsigned char *)ln.mask.p;
-    a.stat_rechecks = (unsigned long long *)ctx->stat.p;
-    UNB_TRY(unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s));
-    UNB_TRY(d2h(ctx, mask, ln.mask.p, m, s));
-    return stat_fetch(ctx, s);
+    return has_neighbour_host(ctx, ctx->region.live, tpts, m, ctx->region.r2, mask);
 }
 
 extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, size_t m,

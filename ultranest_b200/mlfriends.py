@@ -95,7 +95,7 @@ def _friends_of_friends(tpoints, maxradiussq, old_ids):
     """Grow clusters in t-space exactly like the reference (mlfriends.pyx:284-322): a cluster
     keeps absorbing every unassigned point that has a member within the radius; when nothing is
     absorbed the next cluster is seeded at the first unassigned point, or at the first point
-    that carried the new id before.  Each absorption test is one device ``find_nearby``."""
+    that carried the new id before.  Each absorption test is one device any-neighbour scan."""
     eng = _engine()
     n = len(tpoints)
     labels = np.zeros(n, dtype=int_dtype)
@@ -109,7 +109,7 @@ def _friends_of_friends(tpoints, maxradiussq, old_ids):
         free = labels == 0
         if not free.any():
             break
-        hit = eng.find_nearby(tpoints[labels == current, :], tpoints[free, :], maxradiussq) >= 0
+        hit = eng.has_neighbour(tpoints[labels == current, :], tpoints[free, :], maxradiussq)
         if hit.any():
             absorbed = free
             absorbed[free] = hit
