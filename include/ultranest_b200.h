@@ -155,6 +155,12 @@ int unb_region_inside(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
                       int64_t *idx_out);
 int unb_region_inside_dev(unb_ctx *ctx, const double *pts_dev, size_t m, uint8_t *mask_dev,
                           void *stream);
+/* Ellipsoid stage alone against the mirrored ellipsoid, through the same chunked pipeline:
+ * RobustEllipsoidRegion / SimpleRegion / WrappingEllipsoid `.inside` (mlfriends.pyx:1374-1390,
+ * 1628-1649).  Needs only unb_region_set_ellipsoid. */
+int unb_region_inside_ellipsoid(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask);
+int unb_region_inside_ellipsoid_dev(unb_ctx *ctx, const double *pts_dev, size_t m,
+                                    uint8_t *mask_dev, void *stream);
 /* Same pipeline without the ellipsoid stage: transform + neighbour scan of u-space proposals,
  * i.e. `find_nearby(self.unormed, transformLayer.transform(w), ...) >= 0` of
  * sample_from_wrapping_ellipsoid (mlfriends.pyx:1155-1158). */

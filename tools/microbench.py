@@ -110,6 +110,14 @@ def main():
         t_host = time.perf_counter() - t0
         out.append(dict(case="robust_ellipsoid_inside_hostapi", d=d, n_live=n, m=M, s=t_host,
                         points_per_s=M / t_host, accept=float(mask.mean()), bootstrap30_s=t_boot))
+        c_dev = torch.from_numpy(cand).cuda()
+        mk = torch.empty(M, dtype=torch.uint8, device="cuda")
+        ms = timed(lambda: eng.call("unb_region_inside_ellipsoid_dev", c_dev.data_ptr(), M,
+                                    mk.data_ptr(), sh), stream)
+        assert (mk.cpu().numpy().astype(bool) == mask).all()
+        out.append(dict(case="robust_ellipsoid_inside_device", d=d, n_live=n, m=M, ms=ms,
+                        points_per_s=M / ms * 1e3, hbm_gbs=M * (8 * d + 1) / ms / 1e6,
+                        dp_instr_per_s=3.0 * d * d * M / ms * 1e3))
         # configs[2]: eggbox-like multimodal live set d=10, N=2000: rebuild time
         rng = np.random.RandomState(5)
         centres = rng.randint(0, 5, size=(2000, 10)) * 0.2 + 0.1

@@ -69,6 +69,8 @@ SIGNATURES = {
     "unb_region_set_radius": [_dbl],
     "unb_region_inside": [_c_vp, _sz, _c_vp, _c_vp],
     "unb_region_friends": [_c_vp, _sz, _c_vp, _c_vp],
+    "unb_region_inside_ellipsoid": [_c_vp, _sz, _c_vp],
+    "unb_region_inside_ellipsoid_dev": [_c_vp, _sz, _c_vp, _c_vp],
     "unb_region_inside_dev": [_c_vp, _sz, _c_vp, _c_vp],
     "unb_region_find_nearby": [_c_vp, _sz, _c_vp],
     "unb_region_count_nearby": [_c_vp, _sz, _c_vp],
@@ -340,6 +342,13 @@ class Engine(object):
         name = "unb_region_inside" if use_ellipsoid else "unb_region_friends"
         self.call(name, _ptr(p), len(p), _ptr(mask), _ptr(idx))
         return (mask, idx) if want_index else mask
+
+    def region_inside_ellipsoid(self, pts):
+        """Ellipsoid stage alone against the mirrored ellipsoid (chunked host pipeline)."""
+        p = as_f64(pts, 2)
+        mask = np.empty(len(p), dtype=bool)
+        self.call("unb_region_inside_ellipsoid", _ptr(p), len(p), _ptr(mask))
+        return mask
 
     def region_find_nearby(self, tpts):
         p = as_f64(tpts, 2)

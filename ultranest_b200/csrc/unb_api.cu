@@ -664,10 +664,33 @@ int region_ready(unb_ctx *ctx, bool need_ellipsoid)
 }
 
 // enqueue MLFriends.inside (+ optional likelihood) for device-resident rows on lane `ln`
+// ellipsoid membership only (RobustEllipsoidRegion / SimpleRegion / WrappingEllipsoid .inside)
+int enqueue_ellipsoid(unb_ctx *ctx, cudaStream_t s, const double *pts_dev, size_t m,
+                      unsigned char *mask_dev)
+{
+    RegionState &R = ctx->region;
+    const size_t d = R.ell_d;
+    const bool use_const = d <= unb_const_maxd();
+    if (use_const) UNB_TRY(unb_prep_sync_constants(ctx, s));
+    PrepArgs p;
+    memset(&p, 0, sizeof(p));
+    p.pts = pts_dev;
+    p.m = (long long)m;
+    p.d = (int)d;
+    p.center = (const double *)R.ell_center.p;
+    p.invcov = (const double *)R.ell_invcov.p;
+    p.r2 = R.enlarge;
+    p.mask = mask_dev;
+    p.layer_kind = -1;
+    p.use_constants = use_const ? 1 : 0;
+    return unb_launch_prep(ctx, p, s);
+}
+
 int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev, size_t m,
                    unsigned char *mask_dev, long long *idx_dev, double *like_dev,
-                   int loglike_kind, bool use_ellipsoid = true)
+                   int loglike_kind, bool use_ellipsoid = true, bool ellipsoid_only = false)
 {
+    if (ellipsoid_only) return enqueue_ellipsoid(ctx, s, pts_dev, m, mask_dev);
     RegionState &R = ctx->region;
     const size_t d = R.live.d;
     UNB_TRY(unb_reserve(ctx, ln.tcand, m * d * sizeof(double)));
@@ -752,12 +775,13 @@ int upload_lparams(unb_ctx *ctx, int kind, const double *lparams, size_t d, cuda
 
 // chunked, double-buffered host pipeline: H2D(c+1) overlaps kernels(c) and D2H(c)
 int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_t *idx_out,
-                double *like, int loglike_kind, bool use_ellipsoid = true)
+                double *like, int loglike_kind, bool use_ellipsoid = true,
+                bool ellipsoid_only = false)
 {
     RegionState &R = ctx->region;
-    const size_t d = R.live.d;
+    const size_t d = ellipsoid_only ? R.ell_d : R.live.d;
     const size_t rowb = d * sizeof(double);
-    UNB_TRY(unb_live_set_h(ctx, R.live, HMODE_THRESH, R.r2, S0(ctx)));
+    if (!ellipsoid_only) UNB_TRY(unb_live_set_h(ctx, R.live, HMODE_THRESH, R.r2, S0(ctx)));
     UNB_CUDA(ctx, cudaStreamSynchronize(S0(ctx)));
     size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18);
     if (chunk > m) chunk = m;
@@ -790,7 +814,7 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
                                    (unsigned char *)ln.mask.p,
                                    idx_out ? (long long *)ln.idx.p : nullptr,
                                    like ? (double *)ln.like.p : nullptr, loglike_kind,
-                                   use_ellipsoid));
+                                   use_ellipsoid, ellipsoid_only));
             ln.pend_rows = 0;
             if (mask_pinned) {
                 UNB_TRY(d2h(ctx, mask + off, ln.mask.p, rows, s));
@@ -846,6 +870,26 @@ extern "C" int unb_region_inside(unb_ctx *ctx, const double *pts, size_t m, uint
     if (m == 0) return UNB_OK;
     if (!pts || !mask) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     return inside_host(ctx, pts, m, mask, idx_out, nullptr, UNB_LOGLIKE_NONE);
+}
+
+extern "C" int unb_region_inside_ellipsoid(unb_ctx *ctx, const double *pts, size_t m,
+                                           uint8_t *mask)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!ctx->region.have_ellipsoid) return unb_fail(ctx, UNB_ERR_STATE, "region ellipsoid not set");
+    if (m == 0) return UNB_OK;
+    if (!pts || !mask) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    return inside_host(ctx, pts, m, mask, nullptr, nullptr, UNB_LOGLIKE_NONE, true, true);
+}
+
+extern "C" int unb_region_inside_ellipsoid_dev(unb_ctx *ctx, const double *pts_dev, size_t m,
+                                               uint8_t *mask_dev, void *stream)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!ctx->region.have_ellipsoid) return unb_fail(ctx, UNB_ERR_STATE, "region ellipsoid not set");
+    if (m == 0) return UNB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
+    return enqueue_ellipsoid(ctx, s, pts_dev, m, mask_dev);
 }
 
 extern "C" int unb_region_friends(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,

@@ -207,6 +207,7 @@ struct PrepArgs {
     const double *lparams;    // device likelihood parameter block
 };
 int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s);
+size_t unb_const_maxd();
 int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s);
 int unb_launch_transform(unb_ctx *ctx, int kind, bool inverse, const double *in, long long m,
                          int d, const double *shift, const double *mat, double *out,

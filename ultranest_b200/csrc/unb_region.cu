@@ -37,6 +37,14 @@ int set_smem(unb_ctx *ctx, K kernel, size_t bytes)
     return UNB_OK;
 }
 
+// region parameters in __constant__ memory, row stride dr = d rounded up to 4, zero padded
+constexpr int PREP_MAXD = 32;     // register kernel
+constexpr int CONST_MAXD = 56;    // parameters in __constant__ memory (2 x 56^2 doubles = 50 KB)
+__constant__ double c_ell_center[CONST_MAXD];
+__constant__ double c_ell_invcov[CONST_MAXD * CONST_MAXD];
+__constant__ double c_xf_shift[CONST_MAXD];
+__constant__ double c_xf_mat[CONST_MAXD * CONST_MAXD];
+
 // ---------------------------------------------------------------------------------------
 // ellipsoid (+ transform + compaction)
 // ---------------------------------------------------------------------------------------
@@ -52,13 +60,23 @@ __global__ void k_prep(const PrepArgs P)
         double acc = 0.0;
         if (valid) {
             const double *p = P.pts + j * d;
-            for (int k = 0; k < d; k++) my[k] = __dsub_rn(p[k], __ldg(P.center + k));
+            for (int k = 0; k < d; k++)
+                my[k] = __dsub_rn(p[k], P.use_constants ? c_ell_center[k] : __ldg(P.center + k));
             // np.einsum('ij,jk,ik->i'): acc += (d_j * A_jk) * d_k, j outer, k inner
-            for (int jj = 0; jj < d; jj++) {
-                const double dj = my[jj];
-                const double *Arow = P.invcov + (size_t)jj * d;
-                for (int k = 0; k < d; k++)
-                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
+            if (P.use_constants) {   // 32 < d <= 56: matrix through the constant cache (uniform index)
+                const int dr = (d + 3) / 4 * 4;
+                for (int jj = 0; jj < d; jj++) {
+                    const double dj = my[jj];
+                    for (int k = 0; k < d; k++)
+                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, c_ell_invcov[jj * dr + k]), my[k]));
+                }
+            } else {
+                for (int jj = 0; jj < d; jj++) {
+                    const double dj = my[jj];
+                    const double *Arow = P.invcov + (size_t)jj * d;
+                    for (int k = 0; k < d; k++)
+                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
+                }
             }
         }
         inside = valid && (acc <= P.r2);
@@ -101,11 +119,6 @@ __global__ void k_prep(const PrepArgs P)
 // Optionally fuses the vectorised likelihood of the rows that pass the ellipsoid, so the
 // proposals are read from HBM exactly once.
 // ---------------------------------------------------------------------------------------
-constexpr int PREP_MAXD = 32;
-__constant__ double c_ell_center[PREP_MAXD];
-__constant__ double c_ell_invcov[PREP_MAXD * PREP_MAXD];
-__constant__ double c_xf_shift[PREP_MAXD];
-__constant__ double c_xf_mat[PREP_MAXD * PREP_MAXD];
 
 __device__ double np_pairwise_sum(const double *a, int n);
 
@@ -141,8 +154,20 @@ __global__ void __launch_bounds__(128) k_prep_reg(const PrepArgs P)
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = j < P.m;
     double p[DR];
+    if ((d & 1) == 0 && (reinterpret_cast<uintptr_t>(P.pts) & 15) == 0) {
+        // even d: rows are 16-byte aligned, read them as 128-bit loads
+        const double2 *row2 = reinterpret_cast<const double2 *>(P.pts + j * d);
 #pragma unroll
-    for (int k = 0; k < DR; k++) p[k] = (valid && k < d) ? P.pts[j * d + k] : 0.0;
+        for (int k = 0; k < DR; k += 2) {
+            double2 v = make_double2(0.0, 0.0);
+            if (valid && k < d) v = row2[k >> 1];
+            p[k] = v.x;
+            p[k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < DR; k++) p[k] = (valid && k < d) ? P.pts[j * d + k] : 0.0;
+    }
     bool inside = valid;
     if (P.center) {
         double dl[DR];
@@ -412,6 +437,8 @@ int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, c
     return UNB_OK;
 }
 
+size_t unb_const_maxd() { return CONST_MAXD; }
+
 size_t unb_max_rowwise_d() { return ROW_SMEM_BUDGET / sizeof(double) / 32 - 1; }
 
 // -- __constant__ parameter block of the register prep kernel -------------------------------
@@ -434,8 +461,8 @@ int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s)
 {
     RegionState &R = ctx->region;
     if (g_const_owner == ctx && g_const_version == R.param_version) return UNB_OK;
-    const size_t d = R.live.d;
-    if (d > (size_t)PREP_MAXD) return UNB_OK;
+    const size_t d = R.have_ellipsoid ? R.ell_d : R.live.d;
+    if (d > (size_t)CONST_MAXD) return UNB_OK;
     const size_t dr = (d + 3) / 4 * 4;
     // kernels of either lane may still read the old values
     UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
@@ -473,6 +500,8 @@ static int launch_prep_reg(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s)
 int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s)
 {
     if (p.m <= 0) return UNB_OK;
+    if (p.use_constants && p.d > CONST_MAXD)
+        return unb_fail(ctx, UNB_ERR_ARG, "constant-memory prep needs ndim <= %d", CONST_MAXD);
     if (p.use_constants && p.d <= PREP_MAXD) {
         switch ((p.d + 3) / 4 * 4) {
         case 4: return launch_prep_reg<4>(ctx, p, s);

@@ -83,8 +83,12 @@ def compute_mean_pair_distance(pts, clusterids):
 
 def _inside_ellipsoid(points, ellipsoid_center, ellipsoid_invcov, square_radius):
     """``einsum('ij,jk,ik->i', d, invcov, d) <= square_radius`` with ``d = points - center``
-    (mlfriends.pyx:882-912), evaluated in the einsum's own accumulation order.  Bit-exact."""
-    return _engine().inside_ellipsoid(points, ellipsoid_center, ellipsoid_invcov, square_radius)
+    (mlfriends.pyx:882-912), evaluated in the einsum's own accumulation order.  Bit-exact.
+    Runs through the engine's chunked, double-buffered host pipeline."""
+    eng = _engine()
+    pts = _native.as_f64(points, 2)
+    eng.region_set_ellipsoid(ellipsoid_center, ellipsoid_invcov, square_radius)
+    return eng.region_inside_ellipsoid(pts)
 
 
 # ======================================================================================
