@@ -366,6 +366,21 @@ def run_ours(args):
     scan_ms = k0.elapsed_time(k1) / K
     tile_units = eng.stat(_native.STAT_TILE_VISITS)      # of the last launch
     fp64_peak = eng.fp64_peak()                          # lane-FMAs/s, measured on this device
+    fp32_peak = eng.fp32_peak()
+    # same launch with the fp32 pre-filter disabled (pure fp64 filter), for the record
+    eng.set_option(_native.OPT_FILTER_FP32, 0)
+    for _ in range(2):
+        scan_step()
+    torch.cuda.synchronize()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record(stream)
+    for _ in range(K):
+        scan_step()
+    q1.record(stream)
+    torch.cuda.synchronize()
+    scan64_ms = q0.elapsed_time(q1) / K
+    tile_units64 = eng.stat(_native.STAT_TILE_VISITS)
+    eng.set_option(_native.OPT_FILTER_FP32, 1)
     idx_host = idx_dev.cpu().numpy()
     assert ((idx_host >= 0) == mask2_dev.cpu().numpy().astype(bool)).all()
     # pair-dimensions the reference's early-exit loop evaluates for these proposals
@@ -419,14 +434,19 @@ def run_ours(args):
         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
         "traffic": None, "ms_per_launch": scan_ms,
         # compute roofline: this kernel is bound by the fp64 pipe, not by HBM
-        "fp64": {"peak_dfma_per_s": fp64_peak, "peak_source": "measured (unb_fp64_peak, DFMA chains)",
-                 "executed_dfma_per_s": tile_units * 32.0 * 64.0 * NDIM / (scan_ms * 1e-3),
-                 "frac_executed": tile_units * 32.0 * 64.0 * NDIM / (scan_ms * 1e-3) / fp64_peak,
-                 "useful_pair_dims_per_s": scanned * NDIM / (scan_ms * 1e-3),
-                 "frac_useful": scanned * NDIM / (scan_ms * 1e-3) / fp64_peak,
-                 "note": "executed = filter DFMAs actually issued (warp-tiles x lanes); useful = "
-                         "pair-dimensions the reference's early-exit loop evaluates for the same "
-                         "proposals (1 DFMA each here, 3 DP instructions there)"},
+        "compute": {"filter": "fp32 pre-filter + exact fp64 decisions",
+                    "peak_ffma_per_s": fp32_peak, "peak_dfma_per_s": fp64_peak,
+                    "peak_source": "measured on this device (unb_fp32_peak / unb_fp64_peak, FMA chains)",
+                    "executed_ffma_per_s": tile_units * 32.0 * 64.0 * NDIM / (scan_ms * 1e-3),
+                    "frac_of_fp32_peak": tile_units * 32.0 * 64.0 * NDIM / (scan_ms * 1e-3) / fp32_peak,
+                    "useful_pair_dims_per_s": scanned * NDIM / (scan_ms * 1e-3),
+                    "fp64_filter_variant": {
+                        "ms_per_launch": scan64_ms,
+                        "executed_dfma_per_s": tile_units64 * 32.0 * 64.0 * NDIM / (scan64_ms * 1e-3),
+                        "frac_of_fp64_peak": tile_units64 * 32.0 * 64.0 * NDIM / (scan64_ms * 1e-3) / fp64_peak},
+                    "note": "executed = filter FMAs actually issued (warp-tiles x lanes); useful = "
+                            "pair-dimensions the reference's early-exit loop evaluates for the same "
+                            "proposals (3 DP instructions each there)"},
     }
     line = {
         "metric": METRIC, "value": world * M * K / (dev_ms * 1e-3), "unit": "points/s",

@@ -43,6 +43,8 @@ extern "C" {
 #define UNB_OPT_EXACT_ONLY 1     /* 1: bypass the filtered scans, run the plain exact-order
                                     kernels (slow; for validation)                        */
 #define UNB_OPT_CHUNK_ROWS 2     /* rows per H2D/compute/D2H pipeline chunk (host API)    */
+#define UNB_OPT_FILTER_FP32 3    /* 1 (default): the membership kernel pre-filters pairs in
+                                    fp32 (decisions stay exact fp64); 0: fp64 filter only   */
 
 /* unb_ctx_get_stat keys */
 #define UNB_STAT_KERNEL_LAUNCHES 1   /* kernels launched by this ctx since creation       */
@@ -77,6 +79,7 @@ int unb_ctx_synchronize(unb_ctx *ctx);
 /* measured fp64 FMA rate of the device (lane-FMAs per second): the compute-roofline denominator
  * bench.py reports next to the HBM one */
 int unb_fp64_peak(unb_ctx *ctx, double *dfma_per_s);
+int unb_fp32_peak(unb_ctx *ctx, double *ffma_per_s);
 
 /* --------------------------------------------- stateless scans (host buffers) */
 

@@ -305,3 +305,48 @@ def test_inside_and_loglike_fused(eng):
     finally:
         eng.set_option(_native.OPT_CHUNK_ROWS, 0)
     assert (mask2 == mask).all() and (like2[mask] == like[mask]).all()
+
+
+def test_membership_fp32_prefilter_agrees_and_edges(eng):
+    """The any-neighbour kernel with the fp32 pre-filter, with the fp64 filter and the ordered
+    first-index kernel must give the same masks -- including radii set exactly ON reference
+    distances (the `<=` edge) and one ulp below, which the filters may never decide themselves."""
+    from ultranest_b200 import _native
+    rng = np.random.RandomState(77)
+    d = 20
+    a = _live(rng, 4000, d)
+    b = _live(rng, 30000, d, scale=1.1)
+    eng.region_sync_live(a)
+    radii = [_radius_for(a, b, 0.3)]
+    for j in (3, 1234, 20000):           # exact reference distances of real pairs
+        i = int(rng.randint(4000))
+        D = 0.0
+        for k in range(d):
+            diff = a[i, k] - b[j, k]
+            D = D + diff * diff
+        radii += [D, np.nextafter(D, 0)]
+    for r2 in radii:
+        eng.region_set_radius(r2)
+        want = cport.find_nearby(a, b, r2) >= 0
+        assert 0 < want.sum() < len(want)
+        got = {}
+        for flag in (1, 0):
+            eng.set_option(_native.OPT_FILTER_FP32, flag)
+            try:
+                got[flag] = eng.region_has_neighbour(b)
+                rechecks = eng.stat(_native.STAT_RECHECKS)
+            finally:
+                eng.set_option(_native.OPT_FILTER_FP32, 1)
+            assert (got[flag] == want).all(), (r2, flag)
+            # the filter is tight: hardly more exact evaluations than hits
+            assert rechecks <= want.sum() * 1.2 + 256, (rechecks, want.sum())
+        assert ((eng.region_find_nearby(b) >= 0) == want).all()
+    # magnitudes outside the fp32 comfort zone silently take the fp64 filter
+    scale = 1e-20
+    eng.region_sync_live(a * scale)
+    eng.region_set_radius(radii[0] * scale * scale)
+    assert (eng.region_has_neighbour(b * scale) == (cport.find_nearby(a * scale, b * scale, radii[0] * scale * scale) >= 0)).all()
+    # a radius far below the data scale (false-alarm shell too thick for fp32) as well
+    eng.region_sync_live(a)
+    eng.region_set_radius(1e-9)
+    assert (eng.region_has_neighbour(a[:500] + 1e-6) == (cport.find_nearby(a, a[:500] + 1e-6, 1e-9) >= 0)).all()

@@ -21,6 +21,7 @@ UNB_ERR_NUMERIC = -5
 
 OPT_EXACT_ONLY = 1
 OPT_CHUNK_ROWS = 2
+OPT_FILTER_FP32 = 3
 STAT_KERNEL_LAUNCHES = 1
 STAT_RECHECKS = 2
 STAT_H2D_BYTES = 3
@@ -52,6 +53,7 @@ SIGNATURES = {
     "unb_ctx_get_stat": [_int, _c_ip],
     "unb_ctx_synchronize": [],
     "unb_fp64_peak": [_c_dp],
+    "unb_fp32_peak": [_c_dp],
     "unb_find_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_count_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_has_neighbour": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
@@ -204,6 +206,12 @@ class Engine(object):
 
     def synchronize(self):
         self.call("unb_ctx_synchronize")
+
+    def fp32_peak(self):
+        """Measured fp32 FMA rate of this device (lane-FMAs per second)."""
+        v = _dbl(0.0)
+        self.call("unb_fp32_peak", ctypes.byref(v))
+        return float(v.value)
 
     def fp64_peak(self):
         """Measured fp64 FMA rate of this device (lane-FMAs per second)."""

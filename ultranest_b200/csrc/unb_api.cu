@@ -82,7 +82,7 @@ void free_pin(PinBuf &b)
 }
 void free_live(LiveTiles &L)
 {
-    free_dev(L.tiles); free_dev(L.rows); free_dev(L.norms); free_dev(L.namax);
+    free_dev(L.tiles); free_dev(L.rows); free_dev(L.norms); free_dev(L.namax); free_dev(L.tiles32);
     L.valid = false;
 }
 
@@ -150,6 +150,20 @@ ScanArgs scan_args_for(const LiveTiles &L)
     a.kappa = unb_kappa(L.d);
     a.namax_bits = (const unsigned long long *)L.namax.p;
     return a;
+}
+
+// threshold-mode h row + (when safe and enabled) the fp32 image used by the membership kernel
+int prepare_threshold(unb_ctx *ctx, LiveTiles &L, double r2, cudaStream_t s, ScanArgs *a)
+{
+    UNB_TRY(unb_live_set_h(ctx, L, HMODE_THRESH, r2, s));
+    bool ok32 = false;
+    UNB_TRY(unb_live_prepare32(ctx, L, r2, &ok32, s));
+    if (!ok32) L.t32_valid = false;   // never leave a stale image that looks usable
+    if (a && ok32) {
+        a->tiles32 = (const float *)L.tiles32.p;
+        a->kappa32 = unb_kappa32(L.d);
+    }
+    return UNB_OK;
 }
 
 // upload a live block into L and build its tiles
@@ -284,6 +298,7 @@ extern "C" int unb_ctx_set_option(unb_ctx *ctx, int option, int64_t value)
     switch (option) {
     case UNB_OPT_EXACT_ONLY: ctx->exact_only = value ? 1 : 0; return UNB_OK;
     case UNB_OPT_CHUNK_ROWS: ctx->chunk_rows = value > 0 ? value : 0; return UNB_OK;
+    case UNB_OPT_FILTER_FP32: ctx->filter_fp32 = value ? 1 : 0; return UNB_OK;
     default: return unb_fail(ctx, UNB_ERR_ARG, "unknown option %d", option);
     }
 }
@@ -335,6 +350,33 @@ extern "C" int unb_fp64_peak(unb_ctx *ctx, double *dfma_per_s)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *dfma_per_s = best;
+    return UNB_OK;
+}
+
+extern "C" int unb_fp32_peak(unb_ctx *ctx, double *ffma_per_s)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!ffma_per_s) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    cudaStream_t s = S0(ctx);
+    UNB_TRY(unb_reserve(ctx, ctx->aux0, 64));
+    const int blocks = ctx->sm_count * 8, iters = 40000;
+    cudaEvent_t e0, e1;
+    UNB_CUDA(ctx, cudaEventCreate(&e0));
+    UNB_CUDA(ctx, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        UNB_CUDA(ctx, cudaEventRecord(e0, s));
+        UNB_TRY(unb_launch_fp32_peak(ctx, (float *)ctx->aux0.p, blocks, iters, s));
+        UNB_CUDA(ctx, cudaEventRecord(e1, s));
+        UNB_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        UNB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ffma_per_s = best;
     return UNB_OK;
 }
 
@@ -735,6 +777,10 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     a.out_idx = idx_dev;
     if (use_any) {
         a.out_like = fuse_like ? like_dev : nullptr;
+        if (R.live.t32_valid && R.live.t32_r2 == R.r2 && ctx->filter_fp32) {
+            a.tiles32 = (const float *)R.live.tiles32.p;   // prepared by the caller (set_h stage)
+            a.kappa32 = unb_kappa32(R.live.d);
+        }
         UNB_TRY(unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s));
     } else {
         UNB_TRY(unb_launch_scan(ctx, SCAN_FIND, a, 1, s));
@@ -781,7 +827,7 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
     RegionState &R = ctx->region;
     const size_t d = ellipsoid_only ? R.ell_d : R.live.d;
     const size_t rowb = d * sizeof(double);
-    if (!ellipsoid_only) UNB_TRY(unb_live_set_h(ctx, R.live, HMODE_THRESH, R.r2, S0(ctx)));
+    if (!ellipsoid_only) UNB_TRY(prepare_threshold(ctx, R.live, R.r2, S0(ctx), nullptr));
     UNB_CUDA(ctx, cudaStreamSynchronize(S0(ctx)));
     size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18);
     if (chunk > m) chunk = m;
@@ -920,7 +966,7 @@ extern "C" int unb_region_inside_dev(unb_ctx *ctx, const double *pts_dev, size_t
     UNB_TRY(region_ready(ctx, true));
     if (m == 0) return UNB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
-    UNB_TRY(unb_live_set_h(ctx, ctx->region.live, HMODE_THRESH, ctx->region.r2, s));
+    UNB_TRY(prepare_threshold(ctx, ctx->region.live, ctx->region.r2, s, nullptr));
     return enqueue_inside(ctx, ctx->lane[0], s, pts_dev, m, mask_dev, nullptr, nullptr,
                           UNB_LOGLIKE_NONE);
 }
@@ -934,7 +980,7 @@ extern "C" int unb_region_inside_loglike_dev(unb_ctx *ctx, const double *pts_dev
     if (m == 0) return UNB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
     if (lparams) UNB_TRY(upload_lparams(ctx, loglike_kind, lparams, ctx->region.live.d, s));
-    UNB_TRY(unb_live_set_h(ctx, ctx->region.live, HMODE_THRESH, ctx->region.r2, s));
+    UNB_TRY(prepare_threshold(ctx, ctx->region.live, ctx->region.r2, s, nullptr));
     return enqueue_inside(ctx, ctx->lane[0], s, pts_dev, m, mask_dev, nullptr, like_dev,
                           loglike_kind);
 }
@@ -957,7 +1003,9 @@ int has_neighbour_host(unb_ctx *ctx, LiveTiles &L, const double *tpts, size_t m,
     Lane &ln = ctx->lane[0];
     cudaStream_t s = ln.stream;
     const size_t d = L.d;
-    UNB_TRY(unb_live_set_h(ctx, L, HMODE_THRESH, r2, s));
+    ScanArgs pre;
+    memset(&pre, 0, sizeof(pre));
+    UNB_TRY(prepare_threshold(ctx, L, r2, s, &pre));
     UNB_TRY(unb_reserve(ctx, ln.cand, m * d * sizeof(double)));
     UNB_TRY(unb_reserve(ctx, ln.mask, m));
     UNB_TRY(unb_reserve(ctx, ln.counter, 2 * sizeof(int)));
@@ -965,6 +1013,8 @@ int has_neighbour_host(unb_ctx *ctx, LiveTiles &L, const double *tpts, size_t m,
     UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 2 * sizeof(int), s));
     UNB_TRY(stat_reset(ctx, s));
     ScanArgs a = scan_args_for(L);
+    a.tiles32 = pre.tiles32;
+    a.kappa32 = pre.kappa32;
     a.cand = (const double *)ln.cand.p;
     a.n_items = (long long)m;
     a.r2 = r2;
@@ -1012,8 +1062,14 @@ extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, 
     if (m == 0) return UNB_OK;
     if (!tpts_dev || (!nnearby_dev && !mask_dev)) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
-    UNB_TRY(unb_live_set_h(ctx, ctx->region.live, HMODE_THRESH, ctx->region.r2, s));
+    ScanArgs pre;
+    memset(&pre, 0, sizeof(pre));
+    UNB_TRY(prepare_threshold(ctx, ctx->region.live, ctx->region.r2, s, &pre));
     ScanArgs a = scan_args_for(ctx->region.live);
+    if (!nnearby_dev) {
+        a.tiles32 = pre.tiles32;
+        a.kappa32 = pre.kappa32;
+    }
     a.cand = tpts_dev;
     a.n_items = (long long)m;
     a.r2 = ctx->region.r2;

@@ -63,6 +63,11 @@ struct LiveTiles {
     int h_mode = -1;      // which h row is currently stored (HMODE_*)
     double h_r2 = 0.0;
     bool valid = false;
+    // fp32 copy of the tiles for the single-precision pre-filter of the membership kernel
+    DevBuf tiles32;       // ntiles * (dr+1) * tile_n floats, h row built for t32_r2
+    bool t32_valid = false;
+    double t32_r2 = 0.0;
+    double namax_host = 0.0;   // max squared norm, fetched when the fp32 tiles are built
 };
 
 enum { HMODE_NONE = -1, HMODE_THRESH = 0, HMODE_MIN = 1 };
@@ -80,6 +85,8 @@ enum XformKind { XF_NONE = 0, XF_SCALING = 1, XF_AFFINE = 2 };
 struct ScanArgs {
     // live side
     const double *tiles;      // tiled live block (of this launch / of round 0); NULL -> exact kernel
+    const float *tiles32;     // fp32 tiles (membership kernel with the fp32 pre-filter), nullable
+    double kappa32;           // slack factor of the fp32 filter
     const double *live_rows;  // row-major (n x d) live block (plain exact kernel)
     const int *live_idx;      // nullable: exact kernel scans rows live_idx[i] (bootstrap rounds)
     const int *round_live_off;   // nullable: offset of the round's list in live_idx
@@ -156,6 +163,7 @@ struct unb_ctx {
     long long last_rechecks = 0;
     long long last_tile_visits = 0;
     int exact_only = 0;
+    int filter_fp32 = 1;
     long long chunk_rows = 0;
 
     Lane lane[2];
@@ -176,6 +184,10 @@ int unb_live_build(unb_ctx *ctx, LiveTiles &L, const double *rows_dev, size_t n,
 int unb_live_update_rows(unb_ctx *ctx, LiveTiles &L, const int *rows_dev_idx, size_t nrows,
                          cudaStream_t s);
 int unb_live_set_h(unb_ctx *ctx, LiveTiles &L, int h_mode, double r2, cudaStream_t s);
+// builds / refreshes the fp32 tiles for radius r2; *usable says whether the fp32 pre-filter is
+// safe and worthwhile for this block and radius (ranges, slack thin compared with r2)
+int unb_live_prepare32(unb_ctx *ctx, LiveTiles &L, double r2, bool *usable, cudaStream_t s);
+double unb_kappa32(size_t d);
 double unb_kappa(size_t d);
 size_t unb_pick_tile_n(size_t d);
 int unb_launch_scan(unb_ctx *ctx, int mode, const ScanArgs &a, int rounds, cudaStream_t s);
@@ -223,6 +235,7 @@ int unb_launch_pairdist(unb_ctx *ctx, const double *pts, const long long *ids, i
                         double *partial_sum, long long *partial_cnt, cudaStream_t s);
 size_t unb_max_rowwise_d();
 int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, cudaStream_t s);
+int unb_launch_fp32_peak(unb_ctx *ctx, float *scratch, int blocks, int iters, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------
 // device helpers

@@ -427,7 +427,28 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
     if (r == 12345.678) out[0] = r;   // keeps the chains alive
 }
 
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float seed)
+{
+    float a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    float a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; i++) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678f) out[0] = r;
+}
+
 }  // namespace
+
+int unb_launch_fp32_peak(unb_ctx *ctx, float *scratch, int blocks, int iters, cudaStream_t s)
+{
+    k_fp32_peak<<<blocks, 256, 0, s>>>(scratch, iters, 1.0f);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
 
 int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, cudaStream_t s)
 {

@@ -23,6 +23,7 @@
 #include "unb_internal.cuh"
 
 #include <climits>
+#include <cstring>
 
 namespace {
 
@@ -643,6 +644,294 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
 }
 
 // ---------------------------------------------------------------------------------------
+// membership kernel with an fp32 PRE-filter (k_inside_any32)
+//
+// Same persistent / refill / compaction structure as k_inside_any, but the filter runs in single
+// precision: the FFMA pipe issues twice as fast as the DFMA pipe and the candidate registers
+// halve.  Pairs are flagged when  acc32 = h32_i + sum_k fl32(a_ik) fl32(b_jk)  (FFMA chain)
+// reaches thr32_j.  With u32 = 2^-24 every error source (conversion of both operands, the chain,
+// rounding of h and thr) is bounded by (d+4) u32 (|a|^2+|b|^2+r2); h and thr are widened by
+// kappa32 = (4d+32) u32 of the same quantity (h rounded up, thr rounded down), so every
+// reference hit is flagged.  Flagged pairs are DECIDED in the reference's exact fp64 sequence
+// from the fp64 rows in global memory (L2 resident), so the mask is still bit-identical.
+// The host only selects this kernel when the slack is thin compared with r2 and all magnitudes
+// are far from the fp32 range limits; a candidate whose own norm is out of range flags everything.
+// ---------------------------------------------------------------------------------------
+constexpr int any32_min_blocks(int DR, int TM)
+{
+    const int need = TM * DR + 4 * TM + 48;
+    return need <= 96 ? 5 : (need <= 128 ? 4 : (need <= 168 ? 3 : 2));
+}
+
+template <int DR, int TM, int TMA>
+__device__ __forceinline__ void tile_filter32(const float (&a)[TM][DR], const int (&thrkey)[TM],
+                                              unsigned long long (&pend)[TM], const float *T)
+{
+#pragma unroll 1
+    for (int g = 0; g < REG_TILE_N / TN; g++) {
+        const float *Tg = T + g * TN;
+        float acc[TMA][TN];
+        {
+            const float4 h = *reinterpret_cast<const float4 *>(Tg + DR * REG_TILE_N);
+#pragma unroll
+            for (int m = 0; m < TMA; m++) {
+                acc[m][0] = h.x; acc[m][1] = h.y; acc[m][2] = h.z; acc[m][3] = h.w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DR; k++) {
+            const float4 b = *reinterpret_cast<const float4 *>(Tg + k * REG_TILE_N);
+#pragma unroll
+            for (int m = 0; m < TMA; m++) {
+                acc[m][0] = fmaf(a[m][k], b.x, acc[m][0]);
+                acc[m][1] = fmaf(a[m][k], b.y, acc[m][1]);
+                acc[m][2] = fmaf(a[m][k], b.z, acc[m][2]);
+                acc[m][3] = fmaf(a[m][k], b.w, acc[m][3]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < TMA; m++) {
+            unsigned nib = 0;
+#pragma unroll
+            for (int n = 0; n < TN; n++)
+                nib |= (__float_as_int(acc[m][n]) >= thrkey[m]) ? (1u << n) : 0u;
+            pend[m] |= (unsigned long long)nib << (g * TN);
+        }
+    }
+}
+
+template <int DR, int TM>
+__global__ void __launch_bounds__(SCAN_THREADS, any32_min_blocks(DR, TM))
+k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    int *s_info = reinterpret_cast<int *>(smem_raw + 64);
+    constexpr int TILE_FLOATS = (DR + 1) * REG_TILE_N;
+    constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
+    float *tbuf = reinterpret_cast<float *>(smem_raw + 128);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(tbuf + 2 * TILE_FLOATS);   // [DR+4][slots]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const float *tiles = A.tiles32;
+    const int ntiles = (A.n_live + REG_TILE_N - 1) / REG_TILE_N;
+    const int n_items = A.n_items_dev ? *A.n_items_dev : (int)A.n_items;
+    const int d = A.d;
+    const double thr_scale = __dmul_rn(0.5, __dsub_rn(1.0, A.kappa32));
+
+    float a[TM][DR];
+    int row[TM], orow[TM], rem[TM], thrkey[TM], hit[TM];
+    unsigned long long pend[TM];
+#pragma unroll
+    for (int m = 0; m < TM; m++) {
+        row[m] = -1; orow[m] = -1; rem[m] = 0; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull;
+#pragma unroll
+        for (int k = 0; k < DR; k++) a[m][k] = 0.f;
+    }
+    bool exhausted = false;
+
+    auto refill = [&]() {
+#pragma unroll
+        for (int m = 0; m < TM; m++) {
+            if (row[m] >= 0 && (hit[m] || rem[m] <= 0)) {
+                A.out_mask[orow[m]] = hit[m] ? 1 : 0;
+                if (A.out_like && !hit[m]) A.out_like[orow[m]] = -pos_inf();
+                row[m] = -1;
+                thrkey[m] = INT_MAX;
+            }
+            const bool need = (row[m] < 0) && !exhausted;
+            const unsigned ball = __ballot_sync(FULL, need);
+            if (ball) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(queue_head, __popc(ball));
+                base = __shfl_sync(FULL, base, 0);
+                if (need) {
+                    const int item = base + __popc(ball & ((1u << lane) - 1));
+                    if (item < n_items) {
+                        const int r = A.item_idx ? A.item_idx[item] : item;
+                        row[m] = r;
+                        orow[m] = A.out_row_idx ? A.out_row_idx[item] : r;
+                        double nb = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DR; k++) {
+                            const double v = (k < d) ? A.cand[(size_t)r * d + k] : 0.0;
+                            a[m][k] = __double2float_rn(v);
+                            nb = fma(v, v, nb);
+                        }
+                        // threshold rounded DOWN; a zero / out-of-range norm flags everything
+                        const float thr = __double2float_rd(__dmul_rn(nb, thr_scale));
+                        thrkey[m] = (nb < 1e30 && thr > 0.f) ? __float_as_int(thr) : INT_MIN;
+                        rem[m] = ntiles;
+                        hit[m] = 0;
+                    } else {
+                        exhausted = true;
+                    }
+                }
+            }
+        }
+        exhausted = __any_sync(FULL, exhausted);
+    };
+
+    refill();
+    {
+        bool idle = true;
+#pragma unroll
+        for (int m = 0; m < TM; m++) idle &= row[m] < 0;
+        if (__syncthreads_and(idle)) return;
+    }
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
+        tma_bulk_g2s(tbuf, tiles, TILE_BYTES, &bars[0]);
+        mbar_arrive_expect_tx(&bars[1], TILE_BYTES);
+        tma_bulk_g2s(tbuf + TILE_FLOATS, tiles + (size_t)(1 % ntiles) * TILE_FLOATS, TILE_BYTES,
+                     &bars[1]);
+    }
+
+    unsigned long long rechecks = 0;
+    unsigned int tile_units = 0;
+    bool warp_idle = false;
+    bool single = (TM == 1);
+    int cap = SCAN_THREADS * TM;
+    for (unsigned tt = 0;; tt++) {
+        const int buf = tt & 1;
+        mbar_wait(&bars[buf], (tt >> 1) & 1);
+        const float *T = tbuf + buf * TILE_FLOATS;
+        if (!warp_idle) {
+            if (single) {
+                tile_units += 1;
+                tile_filter32<DR, TM, 1>(a, thrkey, pend, T);
+            } else {
+                tile_units += TM;
+                tile_filter32<DR, TM, TM>(a, thrkey, pend, T);
+            }
+            // ---- decide in exact fp64 from the fp64 rows (global memory, L2 resident)
+            const int tile_first = (int)(tt % (unsigned)ntiles) * REG_TILE_N;
+#pragma unroll
+            for (int m = 0; m < TM; m++) {
+                while (__any_sync(FULL, pend[m] != 0ull)) {
+                    if (pend[m] != 0ull) {
+                        const int col = __ffsll((long long)pend[m]) - 1;
+                        pend[m] &= pend[m] - 1ull;
+                        rechecks++;
+                        const double *lp = A.live_rows + (size_t)(tile_first + col) * d;
+                        const double *cp = A.cand + (size_t)row[m] * d;
+                        double D = 0.0;
+                        for (int k = 0; k < d; k++) D = sq_step(D, lp[k], cp[k]);
+                        if (D <= A.r2) {
+                            hit[m] = 1;
+                            thrkey[m] = INT_MAX;
+                            pend[m] = 0ull;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < TM; m++) rem[m]--;
+            refill();
+        }
+        int mine = 0;
+#pragma unroll
+        for (int m = 0; m < TM; m++) mine += row[m] >= 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int *info = s_info + (tt & 1) * (SCAN_THREADS / 32);
+        if (lane == 31) info[warp] = incl | ((exhausted ? 1 : 0) << 16);
+        __syncthreads();
+        int total = 0, warp_off = 0;
+        bool all_exh = true;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; w++) {
+            const int v = info[w];
+            if (w < warp) warp_off += v & 0xffff;
+            total += v & 0xffff;
+            all_exh &= (v >> 16) != 0;
+        }
+        if (total == 0) {
+            mbar_wait(&bars[(tt + 1) & 1], ((tt + 1) >> 1) & 1);
+            break;
+        }
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bars[buf], TILE_BYTES);
+            tma_bulk_g2s(tbuf + buf * TILE_FLOATS,
+                         tiles + (size_t)((tt + 2) % (unsigned)ntiles) * TILE_FLOATS, TILE_BYTES,
+                         &bars[buf]);
+        }
+        if (all_exh && total <= cap / 2 && total <= ANY_STAGE_SLOTS) {
+            int j = warp_off + incl - mine;
+#pragma unroll
+            for (int m = 0; m < TM; m++) {
+                if (row[m] >= 0) {
+#pragma unroll
+                    for (int k = 0; k < DR; k++)
+                        stage[k * ANY_STAGE_SLOTS + j] = (uint32_t)__float_as_int(a[m][k]);
+                    stage[(DR + 0) * ANY_STAGE_SLOTS + j] = (uint32_t)row[m];
+                    stage[(DR + 1) * ANY_STAGE_SLOTS + j] = (uint32_t)orow[m];
+                    stage[(DR + 2) * ANY_STAGE_SLOTS + j] = (uint32_t)rem[m];
+                    stage[(DR + 3) * ANY_STAGE_SLOTS + j] = (uint32_t)thrkey[m];
+                    j++;
+                }
+                row[m] = -1; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull;
+            }
+            __syncthreads();
+            if (tid < total) {
+#pragma unroll
+                for (int k = 0; k < DR; k++)
+                    a[0][k] = __int_as_float((int)stage[k * ANY_STAGE_SLOTS + tid]);
+                row[0] = (int)stage[(DR + 0) * ANY_STAGE_SLOTS + tid];
+                orow[0] = (int)stage[(DR + 1) * ANY_STAGE_SLOTS + tid];
+                rem[0] = (int)stage[(DR + 2) * ANY_STAGE_SLOTS + tid];
+                thrkey[0] = (int)stage[(DR + 3) * ANY_STAGE_SLOTS + tid];
+            }
+            __syncthreads();
+            single = true;
+            cap = (total + 31) / 32 * 32;
+        }
+        bool idle = true;
+#pragma unroll
+        for (int m = 0; m < TM; m++) idle &= row[m] < 0;
+        warp_idle = __all_sync(FULL, idle);
+    }
+    if (A.stat_rechecks) {
+        for (int o = 16; o > 0; o >>= 1) rechecks += __shfl_xor_sync(FULL, rechecks, o);
+        if (lane == 0 && rechecks) atomicAdd(A.stat_rechecks, rechecks);
+    }
+    if (A.stat_tiles && lane == 0) atomicAdd(A.stat_tiles, (unsigned long long)tile_units);
+}
+
+// fp32 image of the tiles: coordinates rounded to nearest, h row for radius r2 rounded UP
+__global__ void k_live_build32(const double *__restrict__ tiles, const double *__restrict__ norms,
+                               int n, int dr, int tile_n, int ntiles, double r2, double kappa32,
+                               float *__restrict__ tiles32)
+{
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= ntiles * tile_n) return;
+    int t = slot / tile_n, c = slot - t * tile_n;
+    const double *T = tiles + (size_t)t * (dr + 1) * tile_n + c;
+    float *F = tiles32 + (size_t)t * (dr + 1) * tile_n + c;
+    for (int k = 0; k < dr; k++) F[(size_t)k * tile_n] = __double2float_rn(T[(size_t)k * tile_n]);
+    float h = -1e30f;
+    if (slot < n) {
+        const double r2w = __dmul_rn(r2, __dadd_rn(1.0, kappa32));
+        const double naw = __dmul_rn(norms[slot], __dsub_rn(1.0, kappa32));
+        h = __double2float_ru(__dmul_rn(0.5, __dsub_rn(r2w, naw)));
+    }
+    F[(size_t)dr * tile_n] = h;
+}
+
+// ---------------------------------------------------------------------------------------
 // generic kernel: any d that fits shared memory; candidates k-major in shared memory,
 // one candidate per thread, 8 live points per register group
 // ---------------------------------------------------------------------------------------
@@ -967,9 +1256,35 @@ int launch_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
     return UNB_OK;
 }
 
+template <int DR, int TM>
+int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
+{
+    const size_t smem = 128 + (2 * (size_t)(DR + 1) * REG_TILE_N + (size_t)(DR + 4) * ANY_STAGE_SLOTS) *
+                                  sizeof(float);
+    UNB_TRY(set_smem(ctx, k_inside_any32<DR, TM>, smem));
+    int per_sm = 0;
+    UNB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inside_any32<DR, TM>,
+                                                               SCAN_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long bx = (a.n_items + SCAN_THREADS * TM - 1) / (SCAN_THREADS * TM);
+    const long long resident = (long long)per_sm * ctx->sm_count;
+    if (bx > resident) bx = resident;
+    if (bx < 1) bx = 1;
+    k_inside_any32<DR, TM><<<(unsigned)bx, SCAN_THREADS, smem, s>>>(a, queue_head);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
 template <int DR>
 int launch_any_tm(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
 {
+    if (a.tiles32) {   // fp32 pre-filter selected by the caller
+        constexpr int TM32 = (DR <= 8) ? 4 : 2;
+        if (a.n_items < (long long)ctx->sm_count * SCAN_THREADS * 2 * TM32)
+            return launch_any32<DR, 1>(ctx, a, queue_head, s);
+        return launch_any32<DR, TM32>(ctx, a, queue_head, s);
+    }
     constexpr int TM_BIG = (DR <= 8) ? 4 : 2;
     if (a.n_items < (long long)ctx->sm_count * SCAN_THREADS * 2 * TM_BIG)
         return launch_any<DR, 1>(ctx, a, queue_head, s);
@@ -1022,6 +1337,7 @@ int unb_live_build(unb_ctx *ctx, LiveTiles &L, const double *rows_dev, size_t n,
                    cudaStream_t s)
 {
     L.valid = false;
+    L.t32_valid = false;
     L.n = n;
     L.d = d;
     L.dr = (d + 3) / 4 * 4;
@@ -1070,6 +1386,7 @@ int unb_live_update_rows(unb_ctx *ctx, LiveTiles &L, const int *rows_dev_idx, si
     ctx->launches++;
     UNB_CUDA(ctx, cudaGetLastError());
     L.h_mode = HMODE_NONE;   // h row of the touched slots is stale
+    L.t32_valid = false;     // and so is the fp32 image
     return UNB_OK;
 }
 
@@ -1085,6 +1402,40 @@ int unb_live_set_h(unb_ctx *ctx, LiveTiles &L, int h_mode, double r2, cudaStream
     UNB_CUDA(ctx, cudaGetLastError());
     L.h_mode = h_mode;
     L.h_r2 = r2;
+    return UNB_OK;
+}
+
+double unb_kappa32(size_t d) { return (4.0 * (double)d + 32.0) * 5.9604644775390625e-08; }
+
+int unb_live_prepare32(unb_ctx *ctx, LiveTiles &L, double r2, bool *usable, cudaStream_t s)
+{
+    *usable = false;
+    if (!ctx->filter_fp32 || ctx->exact_only || L.ntiles == 0 || L.dr > 32 ||
+        L.tile_n != REG_TILE_N)
+        return UNB_OK;
+    if (!L.t32_valid) {   // (re)built block: fetch the largest squared norm once
+        unsigned long long bits = 0;
+        UNB_CUDA(ctx, cudaMemcpyAsync(&bits, L.namax.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
+        UNB_CUDA(ctx, cudaStreamSynchronize(s));
+        memcpy(&L.namax_host, &bits, sizeof(double));
+    }
+    const double k32 = unb_kappa32(L.d);
+    // ranges far from fp32 overflow/underflow, and a shell of false alarms that is thin
+    // compared with the radius (otherwise the fp64 filter is the better tool)
+    if (!(r2 >= 1e-30 && r2 <= 1e30 && L.namax_host <= 1e30)) return UNB_OK;
+    if (!(k32 * (2.0 * L.namax_host + r2) <= r2 / 16.0)) return UNB_OK;
+    if (!L.t32_valid || L.t32_r2 != r2) {
+        const size_t slots = L.ntiles * L.tile_n;
+        UNB_TRY(unb_reserve(ctx, L.tiles32, L.ntiles * (L.dr + 1) * L.tile_n * sizeof(float)));
+        k_live_build32<<<(unsigned)((slots + 127) / 128), 128, 0, s>>>(
+            (const double *)L.tiles.p, (const double *)L.norms.p, (int)L.n, (int)L.dr,
+            (int)L.tile_n, (int)L.ntiles, r2, k32, (float *)L.tiles32.p);
+        ctx->launches++;
+        UNB_CUDA(ctx, cudaGetLastError());
+        L.t32_valid = true;
+        L.t32_r2 = r2;
+    }
+    *usable = true;
     return UNB_OK;
 }
 
