@@ -426,13 +426,26 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+            tr = json.load(f)
+        for name, rec in tr.items():
+            if name.startswith("k_inside_any"):
+                traffic = rec["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     alg_bytes = M * (8.0 * NDIM + 8.0) + N_LIVE * NDIM * 8.0
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_inside_any<20,2> (any-neighbour membership scan)",
+        "bound": "hbm", "kernel": "k_inside_any32<20,2> (any-neighbour membership scan, fp32 pre-filter + fp64 decisions)",
         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-        "traffic": None, "ms_per_launch": scan_ms,
+        "traffic": traffic, "traffic_note": "dram__bytes_read+write per launch, ncu --set full capture "
+                                              "of this command (profiles/kernel_traffic.json); "
+                                              "algorithmic bytes per launch = %.0f" % alg_bytes,
+        "ms_per_launch": scan_ms,
         # compute roofline: this kernel is bound by the fp64 pipe, not by HBM
         "compute": {"filter": "fp32 pre-filter + exact fp64 decisions",
                     "peak_ffma_per_s": fp32_peak, "peak_dfma_per_s": fp64_peak,

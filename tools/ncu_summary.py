@@ -61,5 +61,31 @@ def main(path):
               ", ".join("%s %.2f" % (n, v) for v, n in sorted(stalls, reverse=True)) + "\n")
 
 
+def traffic(path, out_json):
+    """Per-launch DRAM traffic (read + write bytes) of every profiled kernel -> JSON for bench.py."""
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res = {}
+    for r in rows[2:]:
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[col[key]]) * scale.get(units[col[key]], 1.0)
+        name = r[col["Kernel Name"]].split("::")[-1].split("(")[0]
+        res[name] = {"dram_bytes_per_launch": tot, "duration_us_under_ncu":
+                     float(r[col["gpu__time_duration.sum"]]) *
+                     {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(units[col["gpu__time_duration.sum"]], 1.0),
+                     "source": path.split("/")[-1]}
+    with open(out_json, "w") as f:
+        json.dump(res, f, indent=1)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic-json":
+        traffic(sys.argv[1], sys.argv[3])
+    else:
+        main(sys.argv[1])

@@ -660,7 +660,8 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
 constexpr int any32_min_blocks(int DR, int TM)
 {
     const int need = TM * DR + 4 * TM + 48;
-    return need <= 96 ? 5 : (need <= 128 ? 4 : (need <= 168 ? 3 : 2));
+    // (+ ~48 transient registers of the batched fp64 decide loads)
+    return need <= 80 ? 5 : (need <= 128 ? 4 : (need <= 168 ? 3 : 2));
 }
 
 template <int DR, int TM, int TMA>
@@ -824,8 +825,21 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                         rechecks++;
                         const double *lp = A.live_rows + (size_t)(tile_first + col) * d;
                         const double *cp = A.cand + (size_t)row[m] * d;
+                        // loads are issued in batches of 2 x 12 so that one L2 round trip covers
+                        // a batch (the rows are L2 resident); padded terms add +0
                         double D = 0.0;
-                        for (int k = 0; k < d; k++) D = sq_step(D, lp[k], cp[k]);
+#pragma unroll
+                        for (int k0 = 0; k0 < DR; k0 += 12) {
+                            double lv[12], cv[12];
+#pragma unroll
+                            for (int j = 0; j < 12; j++) {
+                                const bool in = (k0 + j) < d;
+                                lv[j] = in ? __ldg(lp + k0 + j) : 0.0;
+                                cv[j] = in ? __ldg(cp + k0 + j) : 0.0;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 12; j++) D = sq_step(D, lv[j], cv[j]);
+                        }
                         if (D <= A.r2) {
                             hit[m] = 1;
                             thrkey[m] = INT_MAX;
