@@ -742,9 +742,14 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     if (idx_dev) UNB_CUDA(ctx, cudaMemsetAsync(idx_dev, 0xff, m * sizeof(long long), s));
     // mask-only requests on a tiled live block go through the register prep kernel (constant
     // memory parameters, fused likelihood) and the persistent any-neighbour kernel
-    const bool use_any = !ctx->exact_only && !idx_dev && R.live.ntiles > 0 && R.live.dr <= 32;
-    const bool fuse_like = use_any && like_dev && loglike_kind != UNB_LOGLIKE_NONE;
-    if (use_any) UNB_TRY(unb_prep_sync_constants(ctx, s));
+    // (d <= 32: register prep kernel; 32 < d <= 128: generic prep kernel + fp32 membership kernel)
+    const bool have32 = R.live.t32_valid && R.live.t32_r2 == R.r2 && ctx->filter_fp32;
+    const bool reg_prep = !ctx->exact_only && !idx_dev && R.live.ntiles > 0 && R.live.dr <= 32;
+    const bool use_any = reg_prep || (!ctx->exact_only && !idx_dev && have32);
+    const bool fuse_like = reg_prep && like_dev && loglike_kind != UNB_LOGLIKE_NONE;
+    // ellipsoid parameters through the constant bank whenever they fit (d <= 56)
+    const bool const_prep = reg_prep || (!ctx->exact_only && R.live.d <= unb_const_maxd());
+    if (const_prep) UNB_TRY(unb_prep_sync_constants(ctx, s));
     PrepArgs p;
     memset(&p, 0, sizeof(p));
     p.pts = pts_dev;
@@ -760,7 +765,7 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     p.tcand = (double *)ln.tcand.p;
     p.items = (int *)ln.items.p;
     p.n_items = (int *)ln.counter.p;
-    p.use_constants = use_any ? 1 : 0;
+    p.use_constants = const_prep ? 1 : 0;
     if (fuse_like) {
         p.like = like_dev;
         p.loglike_kind = loglike_kind;
@@ -777,7 +782,7 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     a.out_idx = idx_dev;
     if (use_any) {
         a.out_like = fuse_like ? like_dev : nullptr;
-        if (R.live.t32_valid && R.live.t32_r2 == R.r2 && ctx->filter_fp32) {
+        if (have32) {
             a.tiles32 = (const float *)R.live.tiles32.p;   // prepared by the caller (set_h stage)
             a.kappa32 = unb_kappa32(R.live.d);
         }

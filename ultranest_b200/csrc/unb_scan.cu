@@ -657,6 +657,8 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
 // The host only selects this kernel when the slack is thin compared with r2 and all magnitudes
 // are far from the fp32 range limits; a candidate whose own norm is out of range flags everything.
 // ---------------------------------------------------------------------------------------
+constexpr int ANY32_MAX_DR = 128;   // candidates of up to 128 dims fit the registers in fp32 (TM = 1)
+
 constexpr int any32_min_blocks(int DR, int TM)
 {
     const int need = TM * DR + 4 * TM + 48;
@@ -925,24 +927,26 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
     if (A.stat_tiles && lane == 0) atomicAdd(A.stat_tiles, (unsigned long long)tile_units);
 }
 
-// fp32 image of the tiles: coordinates rounded to nearest, h row for radius r2 rounded UP
-__global__ void k_live_build32(const double *__restrict__ tiles, const double *__restrict__ norms,
-                               int n, int dr, int tile_n, int ntiles, double r2, double kappa32,
+// fp32 image of the live block, always in 64-point tiles (independent of the fp64 tile size):
+// coordinates rounded to nearest, h row for radius r2 rounded UP
+__global__ void k_live_build32(const double *__restrict__ rows, const double *__restrict__ norms,
+                               int n, int d, int dr, int ntiles, double r2, double kappa32,
                                float *__restrict__ tiles32)
 {
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= ntiles * tile_n) return;
-    int t = slot / tile_n, c = slot - t * tile_n;
-    const double *T = tiles + (size_t)t * (dr + 1) * tile_n + c;
-    float *F = tiles32 + (size_t)t * (dr + 1) * tile_n + c;
-    for (int k = 0; k < dr; k++) F[(size_t)k * tile_n] = __double2float_rn(T[(size_t)k * tile_n]);
+    if (slot >= ntiles * REG_TILE_N) return;
+    int t = slot / REG_TILE_N, c = slot - t * REG_TILE_N;
+    float *F = tiles32 + (size_t)t * (dr + 1) * REG_TILE_N + c;
+    for (int k = 0; k < dr; k++)
+        F[(size_t)k * REG_TILE_N] =
+            (slot < n && k < d) ? __double2float_rn(rows[(size_t)slot * d + k]) : 0.f;
     float h = -1e30f;
     if (slot < n) {
         const double r2w = __dmul_rn(r2, __dadd_rn(1.0, kappa32));
         const double naw = __dmul_rn(norms[slot], __dsub_rn(1.0, kappa32));
         h = __double2float_ru(__dmul_rn(0.5, __dsub_rn(r2w, naw)));
     }
-    F[(size_t)dr * tile_n] = h;
+    F[(size_t)dr * REG_TILE_N] = h;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1312,8 +1316,21 @@ int launch_any_tm(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t
 int unb_launch_inside_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
 {
     if (a.n_items <= 0) return UNB_OK;
-    if (!ctx->exact_only && a.tiles && a.dr <= 32 && a.tile_n == REG_TILE_N && a.out_mask &&
-        !a.out_idx && a.n_live > 0) {
+    const bool mask_only = !ctx->exact_only && a.out_mask && !a.out_idx && a.n_live > 0;
+    if (mask_only && a.tiles32 && a.dr > 32 && a.dr <= ANY32_MAX_DR) {
+        // 32 < d <= 128: fp32 pre-filter kernel only, one candidate per thread
+        switch (a.dr) {
+#define UNB_CASE32(DR_) case DR_: return launch_any32<DR_, 1>(ctx, a, queue_head, s);
+            UNB_CASE32(36) UNB_CASE32(40) UNB_CASE32(44) UNB_CASE32(48) UNB_CASE32(52)
+            UNB_CASE32(56) UNB_CASE32(60) UNB_CASE32(64) UNB_CASE32(68) UNB_CASE32(72)
+            UNB_CASE32(76) UNB_CASE32(80) UNB_CASE32(84) UNB_CASE32(88) UNB_CASE32(92)
+            UNB_CASE32(96) UNB_CASE32(100) UNB_CASE32(104) UNB_CASE32(108) UNB_CASE32(112)
+            UNB_CASE32(116) UNB_CASE32(120) UNB_CASE32(124) UNB_CASE32(128)
+#undef UNB_CASE32
+        default: break;
+        }
+    }
+    if (mask_only && a.dr <= 32 && (a.tiles32 || (a.tiles && a.tile_n == REG_TILE_N))) {
         switch (a.dr) {
         case 4: return launch_any_tm<4>(ctx, a, queue_head, s);
         case 8: return launch_any_tm<8>(ctx, a, queue_head, s);
@@ -1424,8 +1441,8 @@ double unb_kappa32(size_t d) { return (4.0 * (double)d + 32.0) * 5.9604644775390
 int unb_live_prepare32(unb_ctx *ctx, LiveTiles &L, double r2, bool *usable, cudaStream_t s)
 {
     *usable = false;
-    if (!ctx->filter_fp32 || ctx->exact_only || L.ntiles == 0 || L.dr > 32 ||
-        L.tile_n != REG_TILE_N)
+    // needs the squared norms (computed with the fp64 tiles) and candidates that fit registers
+    if (!ctx->filter_fp32 || ctx->exact_only || L.ntiles == 0 || L.dr > ANY32_MAX_DR)
         return UNB_OK;
     if (!L.t32_valid) {   // (re)built block: fetch the largest squared norm once
         unsigned long long bits = 0;
@@ -1439,11 +1456,12 @@ int unb_live_prepare32(unb_ctx *ctx, LiveTiles &L, double r2, bool *usable, cuda
     if (!(r2 >= 1e-30 && r2 <= 1e30 && L.namax_host <= 1e30)) return UNB_OK;
     if (!(k32 * (2.0 * L.namax_host + r2) <= r2 / 16.0)) return UNB_OK;
     if (!L.t32_valid || L.t32_r2 != r2) {
-        const size_t slots = L.ntiles * L.tile_n;
-        UNB_TRY(unb_reserve(ctx, L.tiles32, L.ntiles * (L.dr + 1) * L.tile_n * sizeof(float)));
+        const size_t ntiles32 = (L.n + REG_TILE_N - 1) / REG_TILE_N;
+        const size_t slots = ntiles32 * REG_TILE_N;
+        UNB_TRY(unb_reserve(ctx, L.tiles32, ntiles32 * (L.dr + 1) * REG_TILE_N * sizeof(float)));
         k_live_build32<<<(unsigned)((slots + 127) / 128), 128, 0, s>>>(
-            (const double *)L.tiles.p, (const double *)L.norms.p, (int)L.n, (int)L.dr,
-            (int)L.tile_n, (int)L.ntiles, r2, k32, (float *)L.tiles32.p);
+            (const double *)L.rows.p, (const double *)L.norms.p, (int)L.n, (int)L.d, (int)L.dr,
+            (int)ntiles32, r2, k32, (float *)L.tiles32.p);
         ctx->launches++;
         UNB_CUDA(ctx, cudaGetLastError());
         L.t32_valid = true;
