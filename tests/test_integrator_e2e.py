@@ -77,6 +77,37 @@ def test_gaussian_run_is_identical(swapped_modules):
     assert abs(got2["logz"] - want["logz"]) <= 1e-10 * abs(want["logz"])
 
 
+def test_gaussian20d_run_prefix_is_identical(swapped_modules):
+    """Headline-scale geometry (20-D, 2000 live points, default LocalAffineLayer, clustering,
+    repeated bootstrapped rebuilds, every sampling method the run picks): the first 12 000
+    likelihood calls of a seeded run must be the same run on both region implementations."""
+    from ultranest import ReactiveNestedSampler
+    d, sigma = 20, 0.05
+
+    def loglike(t):
+        return -0.5 * (((t - 0.5) / sigma)**2).sum(axis=1)
+
+    def once():
+        np.random.seed(7)
+        sampler = ReactiveNestedSampler(["p%d" % i for i in range(d)], loglike, transform=transform,
+                                        log_dir=None, vectorized=True)
+        res = sampler.run(min_num_live_points=2000, max_ncalls=12000, viz_callback=False,
+                          show_status=False)
+        return (res["logz"], res["ncall"], res["niter"], sampler.ncall_region,
+                type(sampler.region).__module__, sampler.region.maxradiussq)
+
+    want = once()
+    assert want[4] == "ultranest.mlfriends"
+    import ultranest_b200
+    ultranest_b200.install(force=True)
+    got = once()
+    assert got[4] == "ultranest_b200.mlfriends"
+    assert got[1:4] == want[1:4]
+    assert got[5] == want[5]                       # last bootstrapped radius, bit for bit
+    assert abs(got[0] - want[0]) <= 1e-10 * abs(want[0])
+    assert got[0] == want[0]
+
+
 def test_region_class_argument(swapped_modules):
     """The per-run plug-in point (no module swap): run(region_class=...) +
     sampler.transform_layer_class (integrator.py:2298, 1137)."""
