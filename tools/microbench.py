@@ -86,6 +86,30 @@ def main():
                                             None, mask.data_ptr(), sh), stream)
                 out.append(dict(case="any_size_sweep", d=d, m=msub, ms=ms,
                                 tile_units=eng.stat(_native.STAT_TILE_VISITS)))
+        if d == 20:   # the integrator's per-iteration pattern (integrator.py:1855, 2749-2758)
+            u0 = region.u.copy()
+            t0 = time.perf_counter()
+            nit = 200
+            for i in range(nit):
+                worst = i % len(u0)
+                unew = u0[(i * 7 + 3) % len(u0)] + 1e-4
+                region.u[worst] = unew
+                region.unormed[worst] = region.transformLayer.transform(unew)
+                region.ellipsoid_center = np.mean(region.u, axis=0)
+                ok = region.inside(region.u)
+            per_it = (time.perf_counter() - t0) / nit
+            out.append(dict(case="integrator_iteration_inside_live", d=d, n_live=4000,
+                            us_per_iteration=per_it * 1e6, all_inside=bool(ok.all())))
+            for ndraw in (128, 4096, 65536):
+                for meth in region.sampling_methods:
+                    np.random.seed(1)
+                    meth(nsamples=ndraw)
+                    t0 = time.perf_counter()
+                    for _ in range(10):
+                        got = meth(nsamples=ndraw)
+                    out.append(dict(case="sample", method=meth.__name__, ndraw=ndraw,
+                                    us_per_call=(time.perf_counter() - t0) / 10 * 1e6,
+                                    returned=int(len(got))))
         # fused inside (u-space proposals, mask only)
         p_dev = torch.from_numpy(cand).cuda()
         mask = torch.empty(M, dtype=torch.uint8, device="cuda")
