@@ -67,7 +67,6 @@ __global__ void k_prep(const PrepArgs P)
                 const int dr = (d + 3) / 4 * 4;
                 for (int jj = 0; jj < d; jj++) {
                     const double dj = my[jj];
-#pragma unroll 4
                     for (int k = 0; k < d; k++)
                         acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, c_ell_invcov[jj * dr + k]), my[k]));
                 }
@@ -75,7 +74,6 @@ __global__ void k_prep(const PrepArgs P)
                 for (int jj = 0; jj < d; jj++) {
                     const double dj = my[jj];
                     const double *Arow = P.invcov + (size_t)jj * d;
-#pragma unroll 4
                     for (int k = 0; k < d; k++)
                         acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
                 }
@@ -102,7 +100,6 @@ __global__ void k_prep(const PrepArgs P)
         for (int k = 0; k < d; k++) my[k] = __dsub_rn(p[k], __ldg(P.shift + k));
         for (int jj = 0; jj < d; jj++) {
             double t = 0.0;
-#pragma unroll 4
             for (int k = 0; k < d; k++) t = fma(my[k], __ldg(P.mat + (size_t)k * d + jj), t);
             out[jj] = t;
         }
@@ -244,7 +241,6 @@ __global__ void k_transform(int kind, int inverse, const double *__restrict__ in
             for (int k = 0; k < d; k++) my[k] = __dsub_rn(p[k], __ldg(shift + k));
             for (int jj = 0; jj < d; jj++) {
                 double t = 0.0;
-#pragma unroll 4
                 for (int k = 0; k < d; k++) t = fma(my[k], __ldg(mat + (size_t)k * d + jj), t);
                 o[jj] = t;
             }
@@ -252,7 +248,6 @@ __global__ void k_transform(int kind, int inverse, const double *__restrict__ in
             for (int k = 0; k < d; k++) my[k] = p[k];
             for (int jj = 0; jj < d; jj++) {
                 double t = 0.0;
-#pragma unroll 4
                 for (int k = 0; k < d; k++) t = fma(my[k], __ldg(mat + (size_t)k * d + jj), t);
                 o[jj] = __dadd_rn(t, __ldg(shift + jj));
             }
@@ -376,7 +371,6 @@ __global__ void k_enlargement_f(const double *__restrict__ u, int d,
         double acc = 0.0;
         for (int jj = 0; jj < d; jj++) {
             const double dj = my[jj];
-#pragma unroll 4
             for (int k = 0; k < d; k++)
                 acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(A + (size_t)jj * d + k)), my[k]));
         }
