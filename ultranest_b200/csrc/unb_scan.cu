@@ -516,18 +516,25 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
         if (__syncthreads_and(idle)) return;   // nothing claimed by this block
     }
 
+    // The circular scan may start anywhere.  Start where the block's first proposal sits in the
+    // batch, scaled to the live block: when the proposals ARE the live points in order
+    // (`region.inside(active_u)`, integrator.py:1855) every proposal meets itself within a tile
+    // or two instead of after up to ntiles; for unrelated proposals it is just some offset.
+    if (tid == 0) s_info[8] = orow[0] >= 0 ? orow[0] : 0;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
+    const unsigned start =
+        (unsigned)(((long long)s_info[8] * ntiles) / (A.n_items > 0 ? A.n_items : 1)) % (unsigned)ntiles;
     if (tid == 0) {
         mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
-        tma_bulk_g2s(tbuf, tiles, TILE_BYTES, &bars[0]);
+        tma_bulk_g2s(tbuf, tiles + (size_t)(start % ntiles) * TILE_DOUBLES, TILE_BYTES, &bars[0]);
         mbar_arrive_expect_tx(&bars[1], TILE_BYTES);
-        tma_bulk_g2s(tbuf + TILE_DOUBLES, tiles + (size_t)(1 % ntiles) * TILE_DOUBLES, TILE_BYTES,
-                     &bars[1]);
+        tma_bulk_g2s(tbuf + TILE_DOUBLES, tiles + (size_t)((start + 1) % ntiles) * TILE_DOUBLES,
+                     TILE_BYTES, &bars[1]);
     }
 
     unsigned long long rechecks = 0;
@@ -598,8 +605,8 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
         if (tid == 0) {
             mbar_arrive_expect_tx(&bars[buf], TILE_BYTES);
             tma_bulk_g2s(tbuf + buf * TILE_DOUBLES,
-                         tiles + (size_t)((tt + 2) % (unsigned)ntiles) * TILE_DOUBLES, TILE_BYTES,
-                         &bars[buf]);
+                         tiles + (size_t)((start + tt + 2) % (unsigned)ntiles) * TILE_DOUBLES,
+                         TILE_BYTES, &bars[buf]);
         }
         // ---- drain: once the queue is empty, pack the surviving slots into as few warps as
         // possible (slot m = 0 of threads 0..total-1), so the tail costs lanes, not warps
@@ -785,18 +792,22 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
         if (__syncthreads_and(idle)) return;
     }
 
+    // block-dependent start tile (see k_inside_any)
+    if (tid == 0) s_info[8] = orow[0] >= 0 ? orow[0] : 0;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
+    const unsigned start =
+        (unsigned)(((long long)s_info[8] * ntiles) / (A.n_items > 0 ? A.n_items : 1)) % (unsigned)ntiles;
     if (tid == 0) {
         mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
-        tma_bulk_g2s(tbuf, tiles, TILE_BYTES, &bars[0]);
+        tma_bulk_g2s(tbuf, tiles + (size_t)(start % ntiles) * TILE_FLOATS, TILE_BYTES, &bars[0]);
         mbar_arrive_expect_tx(&bars[1], TILE_BYTES);
-        tma_bulk_g2s(tbuf + TILE_FLOATS, tiles + (size_t)(1 % ntiles) * TILE_FLOATS, TILE_BYTES,
-                     &bars[1]);
+        tma_bulk_g2s(tbuf + TILE_FLOATS, tiles + (size_t)((start + 1) % ntiles) * TILE_FLOATS,
+                     TILE_BYTES, &bars[1]);
     }
 
     unsigned long long rechecks = 0;
@@ -817,7 +828,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                 tile_filter32<DR, TM, TM>(a, thrkey, pend, T);
             }
             // ---- decide in exact fp64 from the fp64 rows (global memory, L2 resident)
-            const int tile_first = (int)(tt % (unsigned)ntiles) * REG_TILE_N;
+            const int tile_first = (int)((start + tt) % (unsigned)ntiles) * REG_TILE_N;
 #pragma unroll
             for (int m = 0; m < TM; m++) {
                 while (__any_sync(FULL, pend[m] != 0ull)) {
@@ -882,8 +893,8 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
         if (tid == 0) {
             mbar_arrive_expect_tx(&bars[buf], TILE_BYTES);
             tma_bulk_g2s(tbuf + buf * TILE_FLOATS,
-                         tiles + (size_t)((tt + 2) % (unsigned)ntiles) * TILE_FLOATS, TILE_BYTES,
-                         &bars[buf]);
+                         tiles + (size_t)((start + tt + 2) % (unsigned)ntiles) * TILE_FLOATS,
+                         TILE_BYTES, &bars[buf]);
         }
         if (all_exh && total <= cap / 2 && total <= ANY_STAGE_SLOTS) {
             int j = warp_off + incl - mine;
@@ -1259,11 +1270,13 @@ int launch_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
 {
     const size_t smem = 128 + (2 * (size_t)(DR + 1) * REG_TILE_N +
                                (size_t)(DR + 2) * ANY_STAGE_SLOTS) * sizeof(double);
-    UNB_TRY(set_smem(ctx, k_inside_any<DR, TM>, smem));
-    int per_sm = 0;
-    UNB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inside_any<DR, TM>,
-                                                               SCAN_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
+    static int per_sm = 0;   // per instantiation; the engine drives one device per process
+    if (per_sm == 0) {
+        UNB_TRY(set_smem(ctx, k_inside_any<DR, TM>, smem));
+        UNB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inside_any<DR, TM>,
+                                                                   SCAN_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
     long long bx = (a.n_items + SCAN_THREADS * TM - 1) / (SCAN_THREADS * TM);
     const long long resident = (long long)per_sm * ctx->sm_count;
     if (bx > resident) bx = resident;
@@ -1279,11 +1292,13 @@ int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t 
 {
     const size_t smem = 128 + (2 * (size_t)(DR + 1) * REG_TILE_N + (size_t)(DR + 4) * ANY_STAGE_SLOTS) *
                                   sizeof(float);
-    UNB_TRY(set_smem(ctx, k_inside_any32<DR, TM>, smem));
-    int per_sm = 0;
-    UNB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inside_any32<DR, TM>,
-                                                               SCAN_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
+    static int per_sm = 0;   // per instantiation; the engine drives one device per process
+    if (per_sm == 0) {
+        UNB_TRY(set_smem(ctx, k_inside_any32<DR, TM>, smem));
+        UNB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inside_any32<DR, TM>,
+                                                                   SCAN_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
     long long bx = (a.n_items + SCAN_THREADS * TM - 1) / (SCAN_THREADS * TM);
     const long long resident = (long long)per_sm * ctx->sm_count;
     if (bx > resident) bx = resident;
