@@ -89,6 +89,42 @@ def test_bootstrap_rewinds_rng_on_failure(ours, ref):
     assert (states[0] == states[1]).all()
 
 
+def _with_restored_integrator(fn):
+    oracle.reference()
+    import ultranest.integrator as integ
+    import ultranest.mlfriends as refmod
+    names = ("AffineLayer", "LocalAffineLayer", "MLFriends", "RobustEllipsoidRegion",
+             "ScalingLayer", "WrappingEllipsoid", "find_nearby")
+    saved = {n: getattr(integ, n) for n in names}
+    fns = [f for cls in vars(integ).values() if isinstance(cls, type)
+           for f in vars(cls).values() if getattr(f, "__defaults__", None)]
+    saved_defaults = [(f, f.__defaults__) for f in fns]
+    try:
+        return fn()
+    finally:
+        for n, v in saved.items():
+            setattr(integ, n, v)
+        for f, d in saved_defaults:
+            f.__defaults__ = d
+        sys.modules["ultranest.mlfriends"] = refmod
+        sys.modules["ultranest"].mlfriends = refmod
+
+
+def test_eggbox_run_on_host_mirror_is_the_reference_run(stub_engine):
+    """Multimodal problem: clustering, cluster-centred LocalAffineLayer, tregion."""
+    def body():
+        want = E.run_eggbox(max_ncalls=5000)
+        assert want["nclusters"] > 1
+        import ultranest_b200
+        ultranest_b200.install(force=True)
+        got = E.run_eggbox(max_ncalls=5000)
+        assert got["region"] == "ultranest_b200.mlfriends"
+        for key in ("niter", "ncall", "ncall_region", "nclusters"):
+            assert got[key] == want[key], key
+        assert abs(got["logz"] - want["logz"]) <= 1e-10 * abs(want["logz"])
+    _with_restored_integrator(body)
+
+
 def test_integrator_run_on_host_mirror_is_the_reference_run(stub_engine):
     """The unmodified integrator over ultranest_b200.mlfriends (kernels = oracle): identical run."""
     oracle.reference()

@@ -108,6 +108,43 @@ def test_gaussian20d_run_prefix_is_identical(swapped_modules):
     assert got[0] == want[0]
 
 
+def eggbox_loglike(z):
+    chi = (np.cos(z / 2.)).prod(axis=1)
+    return (2. + chi)**5
+
+
+def eggbox_transform(x):
+    return x * 10 * np.pi
+
+
+def run_eggbox(ndim=2, nlive=400, max_ncalls=8000):
+    """examples/testeggbox.py: many separated modes -> clustering, cluster-centred layers,
+    id re-use across rebuilds, a transformed-space wrapping ellipsoid (tregion)."""
+    from ultranest import ReactiveNestedSampler
+    np.random.seed(3)
+    sampler = ReactiveNestedSampler(["a", "b", "c", "d"][:ndim], eggbox_loglike,
+                                    transform=eggbox_transform, log_dir=None, vectorized=True)
+    res = sampler.run(min_num_live_points=nlive, max_ncalls=max_ncalls, viz_callback=False,
+                      show_status=False)
+    return dict(logz=res["logz"], ncall=res["ncall"], niter=res["niter"],
+                ncall_region=sampler.ncall_region, nclusters=sampler.transformLayer.nclusters,
+                region=type(sampler.region).__module__,
+                tregion=type(sampler.tregion).__module__ if sampler.tregion is not None else None)
+
+
+def test_eggbox_run_is_identical(swapped_modules):
+    want = run_eggbox()
+    assert want["region"] == "ultranest.mlfriends" and want["nclusters"] > 1
+    import ultranest_b200
+    ultranest_b200.install(force=True)
+    got = run_eggbox()
+    assert got["region"] == "ultranest_b200.mlfriends"
+    assert got["tregion"] in (None, "ultranest_b200.mlfriends")
+    for key in ("niter", "ncall", "ncall_region", "nclusters"):
+        assert got[key] == want[key], key
+    assert abs(got["logz"] - want["logz"]) <= 1e-10 * abs(want["logz"])
+
+
 def test_region_class_argument(swapped_modules):
     """The per-run plug-in point (no module swap): run(region_class=...) +
     sampler.transform_layer_class (integrator.py:2298, 1137)."""
