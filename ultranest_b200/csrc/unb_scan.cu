@@ -23,6 +23,7 @@
 #include "unb_internal.cuh"
 
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -938,6 +939,213 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
     if (A.stat_tiles && lane == 0) atomicAdd(A.stat_tiles, (unsigned long long)tile_units);
 }
 
+// ---------------------------------------------------------------------------------------
+// k_inside_any32w: the same membership scan with WARP-INDEPENDENT streams.  Every warp owns two
+// fp32 tile buffers and two mbarriers, issues its own TMA tile loads (an fp32 tile is 5 KB, so
+// the 4x L2->shared traffic is cheap) and retires / refills / drains on its own: there is no
+// block barrier and no block bookkeeping at all, so a warp that is deciding or refilling never
+// holds up its neighbours.  Drain: once the queue is empty a warp moves the survivors of slot 1
+// into free slot-0 lanes with shuffles and continues with the single-slot filter.
+// ---------------------------------------------------------------------------------------
+template <int DR, int TM>
+__global__ void __launch_bounds__(SCAN_THREADS, any32_min_blocks(DR, TM))
+k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NW = SCAN_THREADS / 32;
+    constexpr int TILE_FLOATS = (DR + 1) * REG_TILE_N;
+    constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + warp * 2;          // 2 per warp
+    float *tbuf = reinterpret_cast<float *>(smem_raw + 128) + (size_t)warp * 2 * TILE_FLOATS;
+    static_assert(NW * 2 * sizeof(uint64_t) <= 128, "mbarrier header");
+
+    const float *tiles = A.tiles32;
+    const int ntiles = (A.n_live + REG_TILE_N - 1) / REG_TILE_N;
+    const int n_items = A.n_items_dev ? *A.n_items_dev : (int)A.n_items;
+    const int d = A.d;
+    const double thr_scale = __dmul_rn(0.5, __dsub_rn(1.0, A.kappa32));
+
+    float a[TM][DR];
+    int row[TM], orow[TM], rem[TM], thrkey[TM], hit[TM];
+    unsigned long long pend[TM];
+#pragma unroll
+    for (int m = 0; m < TM; m++) {
+        row[m] = -1; orow[m] = -1; rem[m] = 0; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull;
+#pragma unroll
+        for (int k = 0; k < DR; k++) a[m][k] = 0.f;
+    }
+    bool exhausted = false;
+
+    auto refill = [&]() {
+#pragma unroll
+        for (int m = 0; m < TM; m++) {
+            if (row[m] >= 0 && (hit[m] || rem[m] <= 0)) {
+                A.out_mask[orow[m]] = hit[m] ? 1 : 0;
+                if (A.out_like && !hit[m]) A.out_like[orow[m]] = -pos_inf();
+                row[m] = -1;
+                thrkey[m] = INT_MAX;
+            }
+            const bool need = (row[m] < 0) && !exhausted;
+            const unsigned ball = __ballot_sync(FULL, need);
+            if (ball) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(queue_head, __popc(ball));
+                base = __shfl_sync(FULL, base, 0);
+                if (need) {
+                    const int item = base + __popc(ball & ((1u << lane) - 1));
+                    if (item < n_items) {
+                        const int r = A.item_idx ? A.item_idx[item] : item;
+                        row[m] = r;
+                        orow[m] = A.out_row_idx ? A.out_row_idx[item] : r;
+                        double nb = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DR; k++) {
+                            const double v = (k < d) ? A.cand[(size_t)r * d + k] : 0.0;
+                            a[m][k] = __double2float_rn(v);
+                            nb = fma(v, v, nb);
+                        }
+                        const float thr = __double2float_rd(__dmul_rn(nb, thr_scale));
+                        thrkey[m] = (nb < 1e30 && thr > 0.f) ? __float_as_int(thr) : INT_MIN;
+                        rem[m] = ntiles;
+                        hit[m] = 0;
+                    } else {
+                        exhausted = true;
+                    }
+                }
+            }
+        }
+        exhausted = __any_sync(FULL, exhausted);
+    };
+
+    refill();
+    {
+        bool idle = true;
+#pragma unroll
+        for (int m = 0; m < TM; m++) idle &= row[m] < 0;
+        if (__all_sync(FULL, idle)) return;   // nothing claimed by this warp
+    }
+
+    // block-dependent start tile (see k_inside_any): here per warp
+    const unsigned start =
+        (unsigned)(((long long)max(__shfl_sync(FULL, orow[0], 0), 0) * ntiles) /
+                   (A.n_items > 0 ? A.n_items : 1)) % (unsigned)ntiles;
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
+        tma_bulk_g2s(tbuf, tiles + (size_t)(start % ntiles) * TILE_FLOATS, TILE_BYTES, &bars[0]);
+        mbar_arrive_expect_tx(&bars[1], TILE_BYTES);
+        tma_bulk_g2s(tbuf + TILE_FLOATS, tiles + (size_t)((start + 1) % ntiles) * TILE_FLOATS,
+                     TILE_BYTES, &bars[1]);
+    }
+    __syncwarp();
+
+    unsigned long long rechecks = 0;
+    unsigned int tile_units = 0;
+    bool single = (TM == 1);   // warp-uniform: every live slot of the warp sits in m = 0
+    for (unsigned tt = 0;; tt++) {
+        const int buf = tt & 1;
+        mbar_wait(&bars[buf], (tt >> 1) & 1);
+        const float *T = tbuf + buf * TILE_FLOATS;
+        if (single) {
+            tile_units += 1;
+            tile_filter32<DR, TM, 1>(a, thrkey, pend, T);
+        } else {
+            tile_units += TM;
+            tile_filter32<DR, TM, TM>(a, thrkey, pend, T);
+        }
+        const int tile_first = (int)((start + tt) % (unsigned)ntiles) * REG_TILE_N;
+#pragma unroll
+        for (int m = 0; m < TM; m++) {
+            while (__any_sync(FULL, pend[m] != 0ull)) {
+                if (pend[m] != 0ull) {
+                    const int col = __ffsll((long long)pend[m]) - 1;
+                    pend[m] &= pend[m] - 1ull;
+                    rechecks++;
+                    const double *lp = A.live_rows + (size_t)(tile_first + col) * d;
+                    const double *cp = A.cand + (size_t)row[m] * d;
+                    double D = 0.0;
+#pragma unroll
+                    for (int k0 = 0; k0 < DR; k0 += 12) {
+                        double lv[12], cv[12];
+#pragma unroll
+                        for (int j = 0; j < 12; j++) {
+                            const bool in = (k0 + j) < d;
+                            lv[j] = in ? __ldg(lp + k0 + j) : 0.0;
+                            cv[j] = in ? __ldg(cp + k0 + j) : 0.0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 12; j++) D = sq_step(D, lv[j], cv[j]);
+                    }
+                    if (D <= A.r2) {
+                        hit[m] = 1;
+                        thrkey[m] = INT_MAX;
+                        pend[m] = 0ull;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < TM; m++) rem[m]--;
+        refill();
+
+        bool idle = true;
+#pragma unroll
+        for (int m = 0; m < TM; m++) idle &= row[m] < 0;
+        if (__all_sync(FULL, idle)) {
+            mbar_wait(&bars[(tt + 1) & 1], ((tt + 1) >> 1) & 1);   // tile tt+1 is always in flight
+            break;
+        }
+        // ---- drain: move the survivors of the upper slots into free slot-0 lanes (shuffles)
+        if (TM > 1 && exhausted && !single) {
+#pragma unroll
+            for (int m = 1; m < TM; m++) {
+                const unsigned free0 = __ballot_sync(FULL, row[0] < 0);
+                const unsigned livem = __ballot_sync(FULL, row[m] >= 0);
+                if (livem != 0u && __popc(livem) <= __popc(free0)) {
+                    // the r-th free lane adopts the slot of the r-th live lane
+                    const bool taker = (free0 >> lane) & 1u;
+                    const int rank = __popc(free0 & ((1u << lane) - 1));
+                    const bool takes = taker && rank < __popc(livem);
+                    const int src = takes ? (int)__fns(livem, 0, rank + 1) : lane;
+#pragma unroll
+                    for (int k = 0; k < DR; k++) {
+                        const float v = __shfl_sync(FULL, a[m][k], src);
+                        if (takes) a[0][k] = v;
+                    }
+                    const int r_ = __shfl_sync(FULL, row[m], src);
+                    const int o_ = __shfl_sync(FULL, orow[m], src);
+                    const int e_ = __shfl_sync(FULL, rem[m], src);
+                    const int t_ = __shfl_sync(FULL, thrkey[m], src);
+                    // which live lanes were adopted: the first popc(livem) free lanes took them all
+                    if (takes) { row[0] = r_; orow[0] = o_; rem[0] = e_; thrkey[0] = t_; hit[0] = 0; pend[0] = 0ull; }
+                    if ((livem >> lane) & 1u) { row[m] = -1; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull; }
+                }
+            }
+            bool upper = false;
+#pragma unroll
+            for (int m = 1; m < TM; m++) upper |= row[m] >= 0;
+            single = !__any_sync(FULL, upper);
+        }
+        __syncwarp();   // every lane is done with tile `buf`
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars[buf], TILE_BYTES);
+            tma_bulk_g2s(tbuf + buf * TILE_FLOATS,
+                         tiles + (size_t)((start + tt + 2) % (unsigned)ntiles) * TILE_FLOATS,
+                         TILE_BYTES, &bars[buf]);
+        }
+    }
+    if (A.stat_rechecks) {
+        for (int o = 16; o > 0; o >>= 1) rechecks += __shfl_xor_sync(FULL, rechecks, o);
+        if (lane == 0 && rechecks) atomicAdd(A.stat_rechecks, rechecks);
+    }
+    if (A.stat_tiles && lane == 0) atomicAdd(A.stat_tiles, (unsigned long long)tile_units);
+}
+
 // fp32 image of the live block, always in 64-point tiles (independent of the fp64 tile size):
 // coordinates rounded to nearest, h row for radius r2 rounded UP
 __global__ void k_live_build32(const double *__restrict__ rows, const double *__restrict__ norms,
@@ -1290,6 +1498,26 @@ int launch_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
 template <int DR, int TM>
 int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
 {
+    static const bool blocksync = getenv("UNB_ANY32_BLOCKSYNC") != nullptr;   // A/B switch
+    long long bx = (a.n_items + SCAN_THREADS * TM - 1) / (SCAN_THREADS * TM);
+    // per-warp tile buffers only pay off while they are small (d <= 32: <= 17 KB per warp)
+    if (!blocksync && DR <= 32) {
+        const size_t smem = 128 + (size_t)(SCAN_THREADS / 32) * 2 * (DR + 1) * REG_TILE_N * sizeof(float);
+        static int per_sm_w = 0;
+        if (per_sm_w == 0) {
+            UNB_TRY(set_smem(ctx, k_inside_any32w<DR, TM>, smem));
+            UNB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                              &per_sm_w, k_inside_any32w<DR, TM>, SCAN_THREADS, smem));
+            if (per_sm_w < 1) per_sm_w = 1;
+        }
+        const long long resident = (long long)per_sm_w * ctx->sm_count;
+        if (bx > resident) bx = resident;
+        if (bx < 1) bx = 1;
+        k_inside_any32w<DR, TM><<<(unsigned)bx, SCAN_THREADS, smem, s>>>(a, queue_head);
+        ctx->launches++;
+        UNB_CUDA(ctx, cudaGetLastError());
+        return UNB_OK;
+    }
     const size_t smem = 128 + (2 * (size_t)(DR + 1) * REG_TILE_N + (size_t)(DR + 4) * ANY_STAGE_SLOTS) *
                                   sizeof(float);
     static int per_sm = 0;   // per instantiation; the engine drives one device per process
@@ -1299,7 +1527,6 @@ int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t 
                                                                    SCAN_THREADS, smem));
         if (per_sm < 1) per_sm = 1;
     }
-    long long bx = (a.n_items + SCAN_THREADS * TM - 1) / (SCAN_THREADS * TM);
     const long long resident = (long long)per_sm * ctx->sm_count;
     if (bx > resident) bx = resident;
     if (bx < 1) bx = 1;
