@@ -407,6 +407,16 @@ def run_ours(args):
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     h2d = (eng.stat(_native.STAT_H2D_BYTES) - h2d0) // K
     d2h = (eng.stat(_native.STAT_D2H_BYTES) - d2h0) // K
+    # the same call with ordinary (pageable) NumPy buffers, as an UltraNest user would pass them
+    def pageable_step():
+        return eng.region_inside_loglike(cand, kind, lparams)
+
+    for _ in range(2):
+        pageable_step()
+    t0 = time.perf_counter()
+    for _ in range(max(K // 2, 1)):
+        pageable_step()
+    pageable_ms = 1e3 * (time.perf_counter() - t0) / max(K // 2, 1)
     clk = clocks.stop()
     e2e_ok = bool((np_mask.view(np.uint8) == mask_dev.cpu().numpy()).all()) if world == 1 else True
 
@@ -477,6 +487,8 @@ def run_ours(args):
         "e2e": {"value": world * M * K / (e2e_ms * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms / K, "matches_device_path": e2e_ok,
+                "pageable_buffers_ms_per_step": pageable_ms,
+                "pageable_buffers_value": M / (pageable_ms * 1e-3),
                 "call": "unb_region_inside_loglike (pinned host buffers, chunked double-buffered)"},
         "gpu_launches": int(launches),
         "roofline": roofline,

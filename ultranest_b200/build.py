@@ -15,7 +15,7 @@ LIBPATH = os.path.join(LIBDIR, "libultranest_b200.so")
 SOURCES = ["unb_api.cu", "unb_region.cu", "unb_scan.cu"]
 HEADERS = ["unb_internal.cuh", os.path.join("..", "..", "include", "ultranest_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+              "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 
 def _nvcc():

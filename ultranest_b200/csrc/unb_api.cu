@@ -9,6 +9,7 @@
 #include <cmath>
 #include <algorithm>
 #include <new>
+#include <thread>
 
 // ---------------------------------------------------------------------------------------
 // infrastructure
@@ -101,6 +102,29 @@ int d2h(unb_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t s)
     UNB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
     ctx->d2h_bytes += (long long)bytes;
     return UNB_OK;
+}
+
+// pageable -> pinned staging copy on several host threads (one thread moves ~10 GB/s, the PCIe
+// link takes 46 GB/s, so a single memcpy would be the bottleneck of the host pipeline)
+void par_memcpy(void *dst, const void *src, size_t bytes)
+{
+    const size_t min_slice = 4u << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nthreads = std::min<size_t>(hw ? std::min(hw, 8u) : 4u, bytes / min_slice);
+    if (nthreads <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t slice = (bytes / nthreads + 63) / 64 * 64;
+    for (size_t t = 1; t < nthreads; t++) {
+        const size_t off = t * slice;
+        if (off >= bytes) break;
+        const size_t len = std::min(slice, bytes - off);
+        pool.emplace_back([=]() { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    memcpy(dst, src, std::min(slice, bytes));
+    for (auto &th : pool) th.join();
 }
 
 bool host_is_pinned(const void *p)
@@ -857,7 +881,7 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
             } else {
                 UNB_TRY(unb_reserve_pinned(ctx, ln.pin_in, chunk * rowb));
                 UNB_CUDA(ctx, cudaEventSynchronize(ln.ev_in));
-                memcpy(ln.pin_in.p, pts + off * d, rows * rowb);
+                par_memcpy(ln.pin_in.p, pts + off * d, rows * rowb);
                 UNB_TRY(h2d(ctx, ln.cand.p, ln.pin_in.p, rows * rowb, s));
                 UNB_CUDA(ctx, cudaEventRecord(ln.ev_in, s));
             }
