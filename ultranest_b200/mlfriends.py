@@ -237,30 +237,30 @@ class ScalingLayer(object):
         """Place the wrap cut of every circular axis in the middle of its largest gap."""
         if not self.has_wraps:
             return
-        self.wrap_cuts = []
-        for i in self.wrapped_dims:
-            vals = np.pad(points[:, i], 1, mode='constant', constant_values=(0, 1))
-            vals.sort()
-            assert vals[0] == 0
-            assert vals[-1] == 1
-            j = (vals[1:] - vals[:-1]).argmax()
-            self.wrap_cuts.append((vals[j] + vals[j + 1]) / 2.)
+        cuts = []
+        for axis in self.wrapped_dims:
+            edges = np.sort(np.concatenate(([0.], points[:, axis], [1.])))
+            assert edges[0] == 0 and edges[-1] == 1
+            widest = np.argmax(edges[1:] - edges[:-1])
+            cuts.append((edges[widest] + edges[widest + 1]) / 2.)
+        self.wrap_cuts = cuts
+
+    def _shift_circular(self, arr, offsets):
+        """``fmod(x + offset, 1)`` on the circular columns of a 2-D copy of ``arr``."""
+        out = arr.copy().reshape((-1, arr.shape[-1]))
+        dims = list(self.wrapped_dims)
+        out[:, dims] = np.fmod(out[:, dims] + np.asarray(offsets), 1)
+        return out
 
     def wrap(self, points):
         if not self.has_wraps:
             return points
-        wpoints = points.copy().reshape((-1, points.shape[-1]))
-        for i, cut in zip(self.wrapped_dims, self.wrap_cuts):
-            wpoints[:, i] = np.fmod(wpoints[:, i] + (1 - cut), 1)
-        return wpoints
+        return self._shift_circular(points, [1 - cut for cut in self.wrap_cuts])
 
     def unwrap(self, wpoints):
         if not self.has_wraps:
             return wpoints
-        points = wpoints.copy().reshape((-1, wpoints.shape[-1]))
-        for i, cut in zip(self.wrapped_dims, self.wrap_cuts):
-            points[:, i] = np.fmod(points[:, i] + cut, 1)
-        return points
+        return self._shift_circular(wpoints, list(self.wrap_cuts))
 
     # -- learning ------------------------------------------------------------------------
     def optimize(self, points, centered_points, clusterids=None, minvol=0.):
@@ -485,20 +485,33 @@ class MLFriends(object):
     """MLFriends region (mlfriends.pyx:915-1257): union of equal-radius balls around the live
     points in the whitened space, intersected with a wrapping ellipsoid."""
 
+    # names of the proposal generators sample() rotates through, in the reference's order
+    _method_names = ("sample_from_transformed_boundingbox", "sample_from_boundingbox",
+                     "sample_from_points", "sample_from_wrapping_ellipsoid")
+
     def __init__(self, u, transformLayer):
-        if not np.logical_and(u > 0, u < 1).all():
-            raise ValueError("not all u values are between 0 and 1: %s"
-                             % u[~np.logical_and(u > 0, u < 1).all()])
+        inside_cube = np.logical_and(u > 0, u < 1)
+        if not inside_cube.all():
+            raise ValueError("not all u values are between 0 and 1: %s" % u[~inside_cube.all()])
         self.u = u
         self.set_transformLayer(transformLayer)
-        self.sampling_methods = [
-            self.sample_from_transformed_boundingbox,
-            self.sample_from_boundingbox,
-            self.sample_from_points,
-            self.sample_from_wrapping_ellipsoid,
-        ]
+        self.sampling_methods = [getattr(self, name) for name in self._method_names]
         self.current_sampling_method = self.sample_from_boundingbox
         self.vol_prefactor = vol_prefactor(self.u.shape[1])
+
+    def _draw_in_wrapping_ellipsoid(self, nsamples):
+        """Uniform draws inside the wrapping ellipsoid (mlfriends.pyx:1145-1154): one
+        ``normal(size=(n, d))`` then one ``uniform(size=(n, 1))`` from the global stream.
+        Returns the draws and the mask of those inside the unit cube."""
+        ndim = self.u.shape[1]
+        z = np.random.normal(size=(nsamples, ndim))
+        sqnorm = (z**2).sum(axis=1)
+        assert (sqnorm > 0).all(), sqnorm
+        z /= (sqnorm**0.5).reshape((nsamples, 1))
+        assert self.enlarge > 0, self.enlarge
+        radial = np.random.uniform(size=(nsamples, 1))**(1. / ndim)
+        w = self.ellipsoid_center + np.dot(z * self.enlarge**0.5 * radial, self.ellipsoid_axes_T)
+        return w, np.logical_and(w > 0, w < 1).all(axis=1)
 
     # -- geometry ------------------------------------------------------------------------
     def estimate_volume(self):
@@ -630,14 +643,7 @@ class MLFriends(object):
     def sample_from_wrapping_ellipsoid(self, nsamples=100):
         """Uniform draws in the wrapping ellipsoid filtered by the friends test
         (mlfriends.pyx:1135-1160)."""
-        N, ndim = self.u.shape
-        z = np.random.normal(size=(nsamples, ndim))
-        assert ((z**2).sum(axis=1) > 0).all(), (z**2).sum(axis=1)
-        z /= ((z**2).sum(axis=1)**0.5).reshape((nsamples, 1))
-        assert self.enlarge > 0, self.enlarge
-        u = z * self.enlarge**0.5 * np.random.uniform(size=(nsamples, 1))**(1. / ndim)
-        w = self.ellipsoid_center + np.dot(u, self.ellipsoid_axes_T)
-        wmask = np.logical_and(w > 0, w < 1).all(axis=1)
+        w, wmask = self._draw_in_wrapping_ellipsoid(nsamples)
         if self._fused_ok():     # transform + neighbour scan in one device pipeline
             vmask = self._bind().region_inside(w[wmask, :], use_ellipsoid=False)
         else:
@@ -709,18 +715,7 @@ class RobustEllipsoidRegion(MLFriends):
     """Single wrapping ellipsoid (mlfriends.pyx:1260-1457): ``inside`` is the Mahalanobis
     filter kernel alone."""
 
-    def __init__(self, u, transformLayer):
-        if not np.logical_and(u > 0, u < 1).all():
-            raise ValueError("not all u values are between 0 and 1: %s"
-                             % u[~np.logical_and(u > 0, u < 1).all()])
-        self.u = u
-        self.set_transformLayer(transformLayer)
-        self.sampling_methods = [
-            self.sample_from_boundingbox,
-            self.sample_from_wrapping_ellipsoid,
-        ]
-        self.current_sampling_method = self.sample_from_boundingbox
-        self.vol_prefactor = vol_prefactor(self.u.shape[1])
+    _method_names = ("sample_from_boundingbox", "sample_from_wrapping_ellipsoid")
 
     def sample_from_boundingbox(self, nsamples=100):
         N, ndim = self.u.shape
@@ -738,14 +733,7 @@ class RobustEllipsoidRegion(MLFriends):
         return w[wmask, :]
 
     def sample_from_wrapping_ellipsoid(self, nsamples=100):
-        N, ndim = self.u.shape
-        z = np.random.normal(size=(nsamples, ndim))
-        assert ((z**2).sum(axis=1) > 0).all(), (z**2).sum(axis=1)
-        z /= ((z**2).sum(axis=1)**0.5).reshape((nsamples, 1))
-        assert self.enlarge > 0, self.enlarge
-        u = z * self.enlarge**0.5 * np.random.uniform(size=(nsamples, 1))**(1. / ndim)
-        w = self.ellipsoid_center + np.dot(u, self.ellipsoid_axes_T)
-        wmask = np.logical_and(w > 0, w < 1).all(axis=1)
+        w, wmask = self._draw_in_wrapping_ellipsoid(nsamples)
         return w[wmask, :]
 
     def inside(self, pts):
