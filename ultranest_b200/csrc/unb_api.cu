@@ -692,6 +692,11 @@ extern "C" int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, cons
         return UNB_OK;   // unchanged since the last call
     R.ell_center_h.assign(center, center + ndim);
     R.ell_invcov_h.assign(invcov, invcov + ndim * ndim);
+    {
+        double fro = 0.0;
+        for (size_t i = 0; i < ndim * ndim; i++) fro += invcov[i] * invcov[i];
+        R.ell_fro = std::sqrt(fro) * (1.0 + 1e-9);
+    }
     R.param_version++;
     UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
     UNB_TRY(unb_reserve(ctx, R.ell_center, ndim * sizeof(double)));
@@ -749,6 +754,7 @@ int enqueue_ellipsoid(unb_ctx *ctx, cudaStream_t s, const double *pts_dev, size_
     p.mask = mask_dev;
     p.layer_kind = -1;
     p.use_constants = use_const ? 1 : 0;
+    p.ell_tol_scale = 2.0 * ((double)(d * d + 2 * d + 8)) * 1.1102230246251565e-16 * R.ell_fro;
     return unb_launch_prep(ctx, p, s);
 }
 
@@ -790,6 +796,7 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     p.items = (int *)ln.items.p;
     p.n_items = (int *)ln.counter.p;
     p.use_constants = const_prep ? 1 : 0;
+    p.ell_tol_scale = 2.0 * ((double)(d * d + 2 * d + 8)) * 1.1102230246251565e-16 * R.ell_fro;
     if (fuse_like) {
         p.like = like_dev;
         p.loglike_kind = loglike_kind;

@@ -133,6 +133,7 @@ struct RegionState {
     bool have_ellipsoid = false;
     size_t ell_d = 0;
     double enlarge = 0.0;
+    double ell_fro = 0.0;     // Frobenius norm of the inverse covariance (ellipsoid filter band)
     DevBuf ell_center, ell_invcov;
     bool have_radius = false;
     double r2 = 0.0;
@@ -214,6 +215,7 @@ struct PrepArgs {
     int *n_items;             // in/out: device counter (must be zeroed)
     // register kernel (d <= 32) only:
     int use_constants;        // ellipsoid / layer parameters come from __constant__ memory
+    double ell_tol_scale;     // 2 (d^2+2d+8) u ||invcov||_F: band half-width per unit |delta|^2 (2x the derived bound)
     double *like;             // out: fused likelihood of the rows inside the ellipsoid (nullable)
     int loglike_kind;
     const double *lparams;    // device likelihood parameter block

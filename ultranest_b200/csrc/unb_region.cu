@@ -173,13 +173,35 @@ __global__ void __launch_bounds__(128) k_prep_reg(const PrepArgs P)
         double dl[DR];
 #pragma unroll
         for (int k = 0; k < DR; k++) dl[k] = __dsub_rn(p[k], c_ell_center[k]);
-        double acc = 0.0;
+        // filter: r_fast = d^T (A d) with fused multiply-adds (d^2 + 2d DFMA instead of the
+        // einsum's 3 d^2 non-fused operations).  Both r_fast and the reference's sequential
+        // einsum value lie within (d^2+2d+4) u * sum|d_j A_jk d_k| <= tol of d^T A d, with
+        // sum|...| <= |d|^2 ||A||_F, so outside the band [r2 - tol, r2 + tol] the comparison
+        // is already decided; inside the band the exact einsum order decides.
+        double nd = 0.0, rfast = 0.0;
 #pragma unroll
-        for (int jj = 0; jj < DR; jj++)
+        for (int jj = 0; jj < DR; jj++) {
+            double y = 0.0;
 #pragma unroll
-            for (int k = 0; k < DR; k++)
-                acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dl[jj], c_ell_invcov[jj * DR + k]), dl[k]));
-        inside = valid && (acc <= P.r2);
+            for (int k = 0; k < DR; k++) y = fma(c_ell_invcov[jj * DR + k], dl[k], y);
+            rfast = fma(dl[jj], y, rfast);
+            nd = fma(dl[jj], dl[jj], nd);
+        }
+        const double tol = __dmul_rn(P.ell_tol_scale, nd);
+        bool in = rfast <= P.r2;
+        const bool band = !(fabs(__dsub_rn(rfast, P.r2)) > tol);   // also true for NaN
+        if (__any_sync(FULL, band && valid)) {
+            if (band) {
+                double acc = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < DR; jj++)
+#pragma unroll
+                    for (int k = 0; k < DR; k++)
+                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dl[jj], c_ell_invcov[jj * DR + k]), dl[k]));
+                in = acc <= P.r2;
+            }
+        }
+        inside = valid && in;
         if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
     }
     if (P.like && valid) {
