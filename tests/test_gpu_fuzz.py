@@ -74,7 +74,7 @@ def test_random_region_inside_case(eng, case):
     from ultranest_b200 import mlfriends as mm
     rng = np.random.RandomState(5000 + case)
     d = int(rng.choice([1, 2, 3, 5, 8, 13, 20, 27, 32, 36]))
-    n = int(rng.choice([max(d + 2, 30), 100, 400, 1000]))
+    n = int(rng.choice([4 * d + 30, 100 + 3 * d, 400, 1000]))   # enough points for non-singular bootstraps
     z = _cloud(rng, n, d, 0)
     A = rng.normal(size=(d, d)) * 0.3 + np.eye(d)
     u = 0.5 + 0.04 * z @ A.T
