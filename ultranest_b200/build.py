@@ -33,12 +33,7 @@ def is_stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    """Compile the CUDA library if missing or older than its sources."""
-    if not force and not is_stale():
-        return LIBPATH
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIBPATH] + SOURCES
+def _run(cmd, verbose):
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -47,6 +42,26 @@ def build(force=False, verbose=False, extra_flags=()):
         raise RuntimeError("nvcc failed building libultranest_b200.so")
     if verbose and res.stdout:
         print(res.stdout)
+
+
+def build(force=False, verbose=False, extra_flags=()):
+    """Compile the CUDA library if missing or older than its sources (one object per source
+    file, so touching one file recompiles only that file)."""
+    if not force and not is_stale():
+        return LIBPATH
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = _nvcc()
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags)
+    header_time = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS
+                      if os.path.exists(os.path.join(CSRC, h)))
+    objects = []
+    for src in SOURCES:
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        src_time = max(os.path.getmtime(os.path.join(CSRC, src)), header_time)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < src_time:
+            _run([nvcc] + compile_flags + ["-c", "-o", obj, src], verbose)
+        objects.append(obj)
+    _run([nvcc, "-shared", "-Xcompiler", "-pthread", "-o", LIBPATH] + objects, verbose)
     return LIBPATH
 
 

@@ -146,8 +146,12 @@ __device__ __forceinline__ double loglike_row(int kind, const double *p, int d, 
     return pow(__dadd_rn(2.0, chi), 5.0);
 }
 
+#ifndef UNB_PREP_MINB
+#define UNB_PREP_MINB 1
+#endif
+
 template <int DR>
-__global__ void __launch_bounds__(128) k_prep_reg(const PrepArgs P)
+__global__ void __launch_bounds__(128, UNB_PREP_MINB) k_prep_reg(const PrepArgs P)
 {
     extern __shared__ __align__(16) double rowbuf[];
     const int d = P.d;
