@@ -224,6 +224,47 @@ int unb_region_inside_loglike_dev(unb_ctx *ctx, const double *pts_dev, size_t m,
                                   uint8_t *mask_dev, double *like_dev, int loglike_kind,
                                   const double *lparams, void *stream);
 
+/* ---- fused refill: ReactiveNestedSampler._refill_samples,
+ * integrator.py:1773-1837, as ONE device pipeline per batch of proposals:
+ *   region membership  (MLFriends.inside, mlfriends.pyx:1186-1211; or the friends test alone for
+ *                       draws that already lie in the wrapping ellipsoid, mlfriends.pyx:1155-1160)
+ *   -> v = transform(u)                       (integrator.py:1790; identity or u*scale+lo)
+ *   -> tregion.inside(v)                      (integrator.py:1793-1796; WrappingEllipsoid.inside,
+ *                                              mlfriends.pyx:1628-1649, all dimensions variable)
+ *   -> logl = loglike(v) for the survivors    (integrator.py:1802-1803), -inf elsewhere
+ *   -> accepted = logl > Lmin                 (integrator.py:1805)
+ * One H2D of the proposals; D2H of one flag byte and one double per row.
+ * flags[j]: bit0 = region member (what region.sample() would have returned),
+ *           bit1 = also inside tregion (a likelihood call was spent: `nc`),
+ *           bit2 = logl > Lmin.
+ * counts[3] = number of rows with bit0 / bit1 / bit2. */
+#define UNB_XFORM_IDENTITY 0
+#define UNB_XFORM_SCALE_SHIFT 1   /* v = u * scale + lo, two roundings like NumPy's `u * scale + lo` */
+
+#define UNB_REFILL_MEMBER 1
+#define UNB_REFILL_TREGION 2
+#define UNB_REFILL_ACCEPTED 4
+
+typedef struct unb_refill_desc {
+    int32_t region_mode;        /* 0: rows are members already (no region test); 1: friends test
+                                   only; 2: wrapping ellipsoid + friends (MLFriends.inside) */
+    int32_t check_cube;         /* rows with a coordinate outside (0,1) are no members
+                                   (mlfriends.pyx:1154) */
+    int32_t xform_kind;         /* UNB_XFORM_* */
+    int32_t loglike_kind;       /* UNB_LOGLIKE_* (not NONE) */
+    const double *xform_scale;  /* [ndim] (SCALE_SHIFT) */
+    const double *xform_lo;     /* [ndim] */
+    const double *treg_center;  /* [ndim]; NULL: no tregion (integrator.py:1797-1800) */
+    const double *treg_invcov;  /* [ndim x ndim] */
+    double treg_enlarge;
+    const double *lparams;      /* as for unb_region_inside_loglike */
+    double Lmin;
+} unb_refill_desc;
+
+int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t ndim,
+                      const unb_refill_desc *desc, uint8_t *flags, double *like,
+                      int64_t *counts);
+
 #ifdef __cplusplus
 }
 #endif

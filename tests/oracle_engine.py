@@ -144,6 +144,39 @@ class OracleEngine(object):
             like[mask] = cport.loglike_eggbox(pts[mask])
         return mask, like
 
+    def _like(self, v, kind, lparams):
+        if kind == _native.LOGLIKE_GAUSS:
+            d = v.shape[1]
+            return cport.loglike_gauss(v, lparams[:d], lparams[d])
+        if kind == _native.LOGLIKE_ROSENBROCK:
+            return cport.loglike_rosenbrock(v)
+        return cport.loglike_eggbox(v)
+
+    def region_refill(self, u, region_mode, check_cube, xform, tregion, like_kind, lparams, Lmin):
+        """Stage by stage what integrator.py:1773-1805 does, with the oracle's pieces."""
+        self.calls += 1
+        u = _native.as_f64(u, 2)
+        n = len(u)
+        if region_mode == 2:
+            member = self.region_inside(u)
+        elif region_mode == 1:
+            member = self.region_inside(u, use_ellipsoid=False)
+        else:
+            member = np.ones(n, dtype=bool)
+        if check_cube:
+            member &= np.logical_and(u > 0, u < 1).all(axis=1)
+        v = u if xform is None else u * xform[0] + xform[1]
+        tpass = member.copy()
+        if tregion is not None and member.any():
+            tpass[member] = cport.inside_ellipsoid(np.ascontiguousarray(v[member]), *tregion)
+        like = np.full(n, -np.inf)
+        if tpass.any():
+            like[tpass] = self._like(np.ascontiguousarray(v[tpass]), like_kind, lparams)
+        acc = like > Lmin
+        flags = (member * _native.REFILL_MEMBER + tpass * _native.REFILL_TREGION
+                 + acc * _native.REFILL_ACCEPTED).astype(np.uint8)
+        return flags, like, (int(member.sum()), int(tpass.sum()), int(acc.sum()))
+
     # -- likelihoods ----------------------------------------------------------------------
     def loglike_gauss(self, theta, centers, sigma, norm_const):
         return cport.loglike_gauss(theta, centers, sigma)

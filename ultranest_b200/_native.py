@@ -37,6 +37,10 @@ LOGLIKE_GAUSS = 1
 LOGLIKE_EGGBOX = 2
 LOGLIKE_ROSENBROCK = 3
 
+XFORM_IDENTITY = 0
+XFORM_SCALE_SHIFT = 1
+REFILL_MEMBER, REFILL_TREGION, REFILL_ACCEPTED = 1, 2, 4
+
 _c_dp = ctypes.POINTER(ctypes.c_double)
 _c_ip = ctypes.POINTER(ctypes.c_int64)
 _c_bp = ctypes.POINTER(ctypes.c_uint8)
@@ -86,6 +90,7 @@ SIGNATURES = {
     "unb_loglike_gauss_dev": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp, _dbl, _dbl, _c_vp],
     "unb_region_inside_loglike": [_c_vp, _sz, _c_vp, _c_vp, _int, _c_vp],
     "unb_region_inside_loglike_dev": [_c_vp, _sz, _c_vp, _c_vp, _int, _c_vp, _c_vp],
+    "unb_region_refill": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp, _c_vp],
 }
 # symbols without the leading ctx argument
 FREE_SIGNATURES = {
@@ -437,6 +442,58 @@ class Engine(object):
         self.call("unb_region_inside_loglike", _ptr(p), len(p), _ptr(mask), _ptr(like),
                   int(kind), _ptr(lp))
         return mask, like
+
+    def region_refill(self, u, region_mode, check_cube, xform, tregion, like_kind, lparams, Lmin):
+        """Fused ``_refill_samples`` stage chain (``unb_region_refill``).  ``xform``: ``None`` or
+        ``(scale, lo)``; ``tregion``: ``None`` or ``(center, invcov, enlarge)``.  Returns
+        ``(flags uint8[n], logl[n], (n_member, n_tregion, n_accepted))``."""
+        p = as_f64(u, 2)
+        n, d = p.shape
+        keep = []
+        desc = RefillDesc()
+        desc.region_mode = int(region_mode)
+        desc.check_cube = 1 if check_cube else 0
+        desc.loglike_kind = int(like_kind)
+        if xform is None:
+            desc.xform_kind = XFORM_IDENTITY
+        else:
+            sc = as_f64(np.broadcast_to(np.asarray(xform[0], dtype=float), (d,)))
+            lo = as_f64(np.broadcast_to(np.asarray(xform[1], dtype=float), (d,)))
+            keep += [sc, lo]
+            desc.xform_kind = XFORM_SCALE_SHIFT
+            desc.xform_scale = _ptr(sc)
+            desc.xform_lo = _ptr(lo)
+        if tregion is not None:
+            ctr = as_f64(tregion[0])
+            inv = as_f64(tregion[1], 2)
+            if ctr.shape != (d,) or inv.shape != (d, d):
+                raise ValueError("tregion ellipsoid does not match ndim=%d" % d)
+            keep += [ctr, inv]
+            desc.treg_center = _ptr(ctr)
+            desc.treg_invcov = _ptr(inv)
+            desc.treg_enlarge = float(tregion[2])
+        if lparams is not None:
+            lp = as_f64(lparams)
+            keep.append(lp)
+            desc.lparams = _ptr(lp)
+        desc.Lmin = float(Lmin)
+        flags = np.empty(n, dtype=np.uint8)
+        like = np.empty(n)
+        counts = np.zeros(3, dtype=np.int64)
+        self.call("unb_region_refill", _ptr(p), n, d, ctypes.addressof(desc), _ptr(flags),
+                  _ptr(like), _ptr(counts))
+        del keep
+        return flags, like, (int(counts[0]), int(counts[1]), int(counts[2]))
+
+
+class RefillDesc(ctypes.Structure):
+    """``unb_refill_desc`` of include/ultranest_b200.h."""
+    _fields_ = [("region_mode", ctypes.c_int32), ("check_cube", ctypes.c_int32),
+                ("xform_kind", ctypes.c_int32), ("loglike_kind", ctypes.c_int32),
+                ("xform_scale", ctypes.c_void_p), ("xform_lo", ctypes.c_void_p),
+                ("treg_center", ctypes.c_void_p), ("treg_invcov", ctypes.c_void_p),
+                ("treg_enlarge", ctypes.c_double), ("lparams", ctypes.c_void_p),
+                ("Lmin", ctypes.c_double)]
 
 
 def _direct_out(out, shape, dtype):

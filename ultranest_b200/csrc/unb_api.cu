@@ -302,7 +302,7 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
     free_dev(ctx->region.layer_shift); free_dev(ctx->region.layer_mat);
     free_dev(ctx->region.ell_center); free_dev(ctx->region.ell_invcov);
     free_dev(ctx->aux0); free_dev(ctx->aux1); free_dev(ctx->aux2); free_dev(ctx->aux3);
-    free_dev(ctx->stat); free_dev(ctx->lparams);
+    free_dev(ctx->stat); free_dev(ctx->lparams); free_dev(ctx->refill_params);
     free_dev(ctx->boot_rows); free_dev(ctx->boot_u); free_dev(ctx->boot_tiles);
     free_dev(ctx->boot_idx); free_dev(ctx->boot_meta); free_dev(ctx->boot_out);
     free_dev(ctx->boot_ell);
@@ -993,6 +993,141 @@ extern "C" int unb_region_inside_loglike(unb_ctx *ctx, const double *pts, size_t
     if (!pts || !mask || !like) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     UNB_TRY(upload_lparams(ctx, loglike_kind, lparams, ctx->region.live.d, S0(ctx)));
     return inside_host(ctx, pts, m, mask, nullptr, like, loglike_kind);
+}
+
+// ---- fused refill (integrator.py:1773-1837) -------------------------------------------------
+extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t ndim,
+                                 const unb_refill_desc *desc, uint8_t *flags, double *like,
+                                 int64_t *counts)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!desc || !counts) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    counts[0] = counts[1] = counts[2] = 0;
+    if (desc->region_mode < 0 || desc->region_mode > 2)
+        return unb_fail(ctx, UNB_ERR_ARG, "region_mode must be 0, 1 or 2");
+    if (desc->xform_kind != UNB_XFORM_IDENTITY && desc->xform_kind != UNB_XFORM_SCALE_SHIFT)
+        return unb_fail(ctx, UNB_ERR_ARG, "unknown transform kind %d", desc->xform_kind);
+    if (desc->xform_kind == UNB_XFORM_SCALE_SHIFT && (!desc->xform_scale || !desc->xform_lo))
+        return unb_fail(ctx, UNB_ERR_ARG, "scale/shift transform needs parameters");
+    if (desc->treg_center && !desc->treg_invcov)
+        return unb_fail(ctx, UNB_ERR_ARG, "tregion needs its inverse covariance");
+    if (desc->loglike_kind == UNB_LOGLIKE_NONE)
+        return unb_fail(ctx, UNB_ERR_ARG, "refill needs a device likelihood");
+    if (ndim == 0 || ndim > unb_max_rowwise_d() / 2)
+        return unb_fail(ctx, UNB_ERR_ARG, "ndim=%zu outside the refill kernel's range", ndim);
+    RegionState &R = ctx->region;
+    if (desc->region_mode != 0) {
+        UNB_TRY(region_ready(ctx, true));
+        if (R.live.d != ndim) return unb_fail(ctx, UNB_ERR_ARG, "ndim does not match the region");
+    }
+    if (m == 0) return UNB_OK;
+    if (!u || !flags || !like) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    const size_t d = ndim;
+    cudaStream_t s0 = S0(ctx);
+    UNB_TRY(upload_lparams(ctx, desc->loglike_kind, desc->lparams, d, s0));
+    // parameter block: scale[d] lo[d] center[d] invcov[d*d] counters(3 ints, padded)
+    const size_t nparam = 3 * d + d * d;
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+    UNB_TRY(unb_reserve(ctx, ctx->refill_params, (nparam + 2) * sizeof(double)));
+    double *P = (double *)ctx->refill_params.p;
+    if (desc->xform_kind == UNB_XFORM_SCALE_SHIFT) {
+        UNB_TRY(h2d(ctx, P, desc->xform_scale, d * sizeof(double), s0));
+        UNB_TRY(h2d(ctx, P + d, desc->xform_lo, d * sizeof(double), s0));
+    }
+    if (desc->treg_center) {
+        UNB_TRY(h2d(ctx, P + 2 * d, desc->treg_center, d * sizeof(double), s0));
+        UNB_TRY(h2d(ctx, P + 3 * d, desc->treg_invcov, d * d * sizeof(double), s0));
+    }
+    int *cnt_dev = (int *)(P + nparam);
+    UNB_CUDA(ctx, cudaMemsetAsync(cnt_dev, 0, 4 * sizeof(int), s0));
+    if (desc->region_mode != 0) UNB_TRY(prepare_threshold(ctx, R.live, R.r2, s0, nullptr));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s0));
+
+    const size_t rowb = d * sizeof(double);
+    size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18);
+    if (chunk > m) chunk = m;
+    const bool src_pinned = host_is_pinned(u);
+    const bool flags_pinned = host_is_pinned(flags);
+    const bool like_pinned = host_is_pinned(like);
+    int rc = UNB_OK;
+    size_t c = 0;
+    for (size_t off = 0; off < m && rc == UNB_OK; off += chunk, c++) {
+        const size_t rows = std::min(chunk, m - off);
+        Lane &ln = ctx->lane[c & 1];
+        cudaStream_t s = ln.stream;
+        lane_flush(ln);
+        auto body = [&]() -> int {
+            UNB_TRY(unb_reserve(ctx, ln.cand, chunk * rowb));
+            UNB_TRY(unb_reserve(ctx, ln.mask, chunk));
+            UNB_TRY(unb_reserve(ctx, ln.like, chunk * sizeof(double)));
+            if (src_pinned) {
+                UNB_TRY(h2d(ctx, ln.cand.p, u + off * d, rows * rowb, s));
+            } else {
+                UNB_TRY(unb_reserve_pinned(ctx, ln.pin_in, chunk * rowb));
+                UNB_CUDA(ctx, cudaEventSynchronize(ln.ev_in));
+                par_memcpy(ln.pin_in.p, u + off * d, rows * rowb);
+                UNB_TRY(h2d(ctx, ln.cand.p, ln.pin_in.p, rows * rowb, s));
+                UNB_CUDA(ctx, cudaEventRecord(ln.ev_in, s));
+            }
+            if (desc->region_mode != 0)
+                UNB_TRY(enqueue_inside(ctx, ln, s, (const double *)ln.cand.p, rows,
+                                       (unsigned char *)ln.mask.p, nullptr, nullptr,
+                                       UNB_LOGLIKE_NONE, desc->region_mode == 2, false));
+            TailArgs t;
+            memset(&t, 0, sizeof(t));
+            t.pts = (const double *)ln.cand.p;
+            t.m = (long long)rows;
+            t.d = (int)d;
+            t.flags = (unsigned char *)ln.mask.p;
+            t.have_mask = desc->region_mode != 0;
+            t.check_cube = desc->check_cube;
+            t.xform_kind = desc->xform_kind;
+            t.xform_scale = P;
+            t.xform_lo = P + d;
+            t.treg_center = desc->treg_center ? P + 2 * d : nullptr;
+            t.treg_invcov = P + 3 * d;
+            t.treg_r2 = desc->treg_enlarge;
+            t.loglike_kind = desc->loglike_kind;
+            t.lparams = (const double *)ctx->lparams.p;
+            t.Lmin = desc->Lmin;
+            t.like = (double *)ln.like.p;
+            t.counts = cnt_dev;
+            UNB_TRY(unb_launch_refill_tail(ctx, t, s));
+            ln.pend_rows = 0;
+            if (flags_pinned) {
+                UNB_TRY(d2h(ctx, flags + off, ln.mask.p, rows, s));
+            } else {
+                UNB_TRY(unb_reserve_pinned(ctx, ln.pin_mask, chunk));
+                UNB_TRY(d2h(ctx, ln.pin_mask.p, ln.mask.p, rows, s));
+                ln.pend_mask = flags + off;
+                ln.pend_rows = rows;
+            }
+            if (like_pinned) {
+                UNB_TRY(d2h(ctx, like + off, ln.like.p, rows * sizeof(double), s));
+            } else {
+                UNB_TRY(unb_reserve_pinned(ctx, ln.pin_like, chunk * sizeof(double)));
+                UNB_TRY(d2h(ctx, ln.pin_like.p, ln.like.p, rows * sizeof(double), s));
+                ln.pend_like = like + off;
+                ln.pend_rows = rows;
+            }
+            UNB_CUDA(ctx, cudaEventRecord(ln.ev_done, s));
+            return UNB_OK;
+        };
+        rc = body();
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaStreamSynchronize(ctx->lane[i].stream);
+        lane_flush(ctx->lane[i]);
+    }
+    if (rc != UNB_OK) return rc;
+    int cnt_host[4] = {0, 0, 0, 0};
+    UNB_TRY(d2h(ctx, cnt_host, cnt_dev, 3 * sizeof(int), s0));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s0));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return unb_fail(ctx, UNB_ERR_CUDA, "refill pipeline: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 3; i++) counts[i] = cnt_host[i];
+    return UNB_OK;
 }
 
 extern "C" int unb_region_inside_dev(unb_ctx *ctx, const double *pts_dev, size_t m,

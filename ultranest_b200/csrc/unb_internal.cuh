@@ -172,6 +172,7 @@ struct unb_ctx {
     LiveTiles scratch_live;          // stateless calls
     DevBuf aux0, aux1, aux2, aux3, stat;
     DevBuf lparams;                  // likelihood parameters
+    DevBuf refill_params;            // fused refill: xform scale/lo, tregion center/invcov, counters
     // bootstrap scratch
     DevBuf boot_rows, boot_u, boot_tiles, boot_idx, boot_meta, boot_out, boot_ell;
     PinBuf pin_small;
@@ -223,6 +224,25 @@ struct PrepArgs {
 int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s);
 size_t unb_const_maxd();
 int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s);
+// tail of the fused refill (integrator.py:1790-1805): user transform, tregion, likelihood, Lmin
+struct TailArgs {
+    const double *pts;           // (m x d) proposals, u-space
+    long long m;
+    int d;
+    unsigned char *flags;        // in: region membership byte (ignored when !have_mask); out: flag bits
+    int have_mask;
+    int check_cube;
+    int xform_kind;
+    const double *xform_scale, *xform_lo;
+    const double *treg_center, *treg_invcov;   // nullable
+    double treg_r2;
+    int loglike_kind;
+    const double *lparams;
+    double Lmin;
+    double *like;                // out
+    int *counts;                 // [3] member / tregion / accepted (atomically incremented)
+};
+int unb_launch_refill_tail(unb_ctx *ctx, const TailArgs &t, cudaStream_t s);
 int unb_launch_transform(unb_ctx *ctx, int kind, bool inverse, const double *in, long long m,
                          int d, const double *shift, const double *mat, double *out,
                          cudaStream_t s);

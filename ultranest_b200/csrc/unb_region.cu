@@ -371,6 +371,62 @@ __global__ void k_loglike(int kind, const double *__restrict__ params, int d, lo
 }
 
 // ---------------------------------------------------------------------------------------
+// tail of the fused refill: for every region member  v = transform(u)  ->  tregion.inside(v)
+// (einsum order of _inside_ellipsoid)  ->  loglike(v)  ->  logl > Lmin.  Per thread two
+// shared-memory rows: v and the likelihood's term vector.
+// ---------------------------------------------------------------------------------------
+__global__ void k_refill_tail(const TailArgs T)
+{
+    extern __shared__ __align__(16) double rowbuf[];
+    const int d = T.d, ds = odd_stride(d);
+    double *v = rowbuf + (size_t)threadIdx.x * 2 * ds;
+    double *t = v + ds;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = j < T.m;
+    bool member = false, tpass = false, accepted = false;
+    if (valid) {
+        const double *p = T.pts + j * d;
+        member = T.have_mask ? (T.flags[j] != 0) : true;
+        if (member && T.check_cube)
+            for (int k = 0; k < d; k++) member = member && (p[k] > 0.0) && (p[k] < 1.0);
+        double like = -__longlong_as_double(0x7ff0000000000000LL);
+        if (member) {
+            if (T.xform_kind == UNB_XFORM_SCALE_SHIFT)
+                for (int k = 0; k < d; k++)
+                    v[k] = __dadd_rn(__dmul_rn(p[k], __ldg(T.xform_scale + k)), __ldg(T.xform_lo + k));
+            else
+                for (int k = 0; k < d; k++) v[k] = p[k];
+            tpass = true;
+            if (T.treg_center) {
+                for (int k = 0; k < d; k++) t[k] = __dsub_rn(v[k], __ldg(T.treg_center + k));
+                double acc = 0.0;
+                for (int jj = 0; jj < d; jj++) {
+                    const double dj = t[jj];
+                    const double *Arow = T.treg_invcov + (size_t)jj * d;
+                    for (int k = 0; k < d; k++)
+                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), t[k]));
+                }
+                tpass = acc <= T.treg_r2;
+            }
+            if (tpass) {
+                like = loglike_row(T.loglike_kind, v, d, t, T.lparams);
+                accepted = like > T.Lmin;
+            }
+        }
+        T.like[j] = like;
+        T.flags[j] = (unsigned char)((member ? UNB_REFILL_MEMBER : 0) | (tpass ? UNB_REFILL_TREGION : 0) |
+                                     (accepted ? UNB_REFILL_ACCEPTED : 0));
+    }
+    const unsigned bm = __ballot_sync(FULL, member), bt = __ballot_sync(FULL, tpass),
+                   ba = __ballot_sync(FULL, accepted);
+    if ((threadIdx.x & 31) == 0) {
+        if (bm) atomicAdd(T.counts + 0, __popc(bm));
+        if (bt) atomicAdd(T.counts + 1, __popc(bt));
+        if (ba) atomicAdd(T.counts + 2, __popc(ba));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // bootstrap enlargement: per round, max over the left-out rows of the einsum form
 // ---------------------------------------------------------------------------------------
 __global__ void k_enlargement_f(const double *__restrict__ u, int d,
@@ -599,6 +655,19 @@ int unb_launch_loglike(unb_ctx *ctx, int kind, const double *params, int d, long
     UNB_TRY(set_smem(ctx, k_loglike, smem));
     k_loglike<<<(unsigned)((n + threads - 1) / threads), threads, smem, s>>>(
         kind, params, d, n, like, mask, lparams_dev);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
+    return UNB_OK;
+}
+
+int unb_launch_refill_tail(unb_ctx *ctx, const TailArgs &t, cudaStream_t s)
+{
+    if (t.m <= 0) return UNB_OK;
+    const int threads = row_threads(2 * odd_stride(t.d) + 1);
+    if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%d too large for the row kernels", t.d);
+    const size_t smem = (size_t)threads * 2 * odd_stride(t.d) * sizeof(double);
+    UNB_TRY(set_smem(ctx, k_refill_tail, smem));
+    k_refill_tail<<<(unsigned)((t.m + threads - 1) / threads), threads, smem, s>>>(t);
     ctx->launches++;
     UNB_CUDA(ctx, cudaGetLastError());
     return UNB_OK;

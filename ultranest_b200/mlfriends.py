@@ -499,7 +499,7 @@ class MLFriends(object):
         self.current_sampling_method = self.sample_from_boundingbox
         self.vol_prefactor = vol_prefactor(self.u.shape[1])
 
-    def _draw_in_wrapping_ellipsoid(self, nsamples):
+    def _draw_in_wrapping_ellipsoid(self, nsamples, want_mask=True):
         """Uniform draws inside the wrapping ellipsoid (mlfriends.pyx:1145-1154): one
         ``normal(size=(n, d))`` then one ``uniform(size=(n, 1))`` from the global stream.
         Returns the draws and the mask of those inside the unit cube."""
@@ -511,7 +511,7 @@ class MLFriends(object):
         assert self.enlarge > 0, self.enlarge
         radial = np.random.uniform(size=(nsamples, 1))**(1. / ndim)
         w = self.ellipsoid_center + np.dot(z * self.enlarge**0.5 * radial, self.ellipsoid_axes_T)
-        return w, np.logical_and(w > 0, w < 1).all(axis=1)
+        return w, (np.logical_and(w > 0, w < 1).all(axis=1) if want_mask else None)
 
     # -- geometry ------------------------------------------------------------------------
     def estimate_volume(self):
@@ -650,6 +650,29 @@ class MLFriends(object):
             v = self.transformLayer.transform(w[wmask, :])
             vmask = self._bind(need_ellipsoid=False).region_has_neighbour(v)
         return w[wmask, :][vmask, :]
+
+    def _propose(self, nsamples):
+        """First half of :meth:`sample` for the fused refill (:mod:`ultranest_b200.refill`):
+        consume the RNG exactly like the current sampling method, but hand the membership test
+        to the caller's device pipeline.  Returns ``(rows, region_mode, check_cube)`` with
+        ``region_mode`` 2 = rows still need ``inside()`` (bounding-box draws,
+        mlfriends.pyx:1096-1112), 1 = rows lie in the wrapping ellipsoid and need the cube and
+        friends tests (mlfriends.pyx:1154-1160), 0 = rows are finished region samples."""
+        method = getattr(self.current_sampling_method, '__func__', None)
+        if self._fused_ok():
+            if method is MLFriends.sample_from_boundingbox:
+                N, ndim = self.u.shape
+                return np.random.uniform(size=(nsamples, ndim)), 2, False
+            if method is MLFriends.sample_from_wrapping_ellipsoid:
+                w, _ = self._draw_in_wrapping_ellipsoid(nsamples, want_mask=False)
+                return w, 1, True
+        return self.sample(nsamples=nsamples), 0, False
+
+    def _after_sample(self, nfound):
+        """Second half of :meth:`sample`: method switch on an empty draw (mlfriends.pyx:1180-1183)."""
+        if nfound == 0:
+            self.current_sampling_method = \
+                self.sampling_methods[np.random.randint(len(self.sampling_methods))]
 
     def sample(self, nsamples=100):
         """Draw from the region with the current method; switch method at random when a draw
