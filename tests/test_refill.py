@@ -238,17 +238,22 @@ def test_device_refill_matches_oracle_chain(ndim, nlive):
     u = base + rng.normal(size=(n, ndim)) * 0.02 * rng.uniform(0, 3, size=(n, 1))
     u[::97] += 1.0
     scale, lo = np.linspace(1.0, 4.0, ndim), np.linspace(-2.0, 1.0, ndim)
-    v_live = region.u * scale + lo
-    cov = np.cov(v_live, rowvar=False) + 1e-12 * np.eye(ndim)
-    treg = (v_live.mean(axis=0), np.linalg.inv(cov), float(ndim) * 1.2)
-    centers = v_live.mean(axis=0)
-    lparams = np.concatenate([centers, [0.3, 0.5 * np.log(2 * np.pi * 0.3**2) * ndim]])
-    cases = [(_native.LOGLIKE_GAUSS, lparams), (_native.LOGLIKE_ROSENBROCK, None)]
+
+    def ellipsoid_of(pts):     # transformed-space ellipsoid that cuts some members off
+        cov = np.cov(pts, rowvar=False) + 1e-12 * np.eye(ndim)
+        return pts.mean(axis=0), np.linalg.inv(cov), float(ndim) * 1.2
+
+    tregs = {False: ellipsoid_of(region.u), True: ellipsoid_of(region.u * scale + lo)}
+    lps = {False: np.concatenate([region.u.mean(axis=0), [0.05, 0.5 * np.log(2 * np.pi * 0.05**2) * ndim]]),
+           True: np.concatenate([(region.u * scale + lo).mean(axis=0),
+                                 [0.3, 0.5 * np.log(2 * np.pi * 0.3**2) * ndim]])}
     for mode in (0, 1, 2):
         for check_cube in (False, True):
             for xform in (None, (scale, lo)):
-                for tregion in (None, treg):
-                    like_kind, lp = cases[(mode + (xform is None)) % 2]
+                for tregion in (None, tregs[xform is not None]):
+                    cases = [(_native.LOGLIKE_GAUSS, lps[xform is not None]),
+                             (_native.LOGLIKE_ROSENBROCK, None)]
+                    like_kind, lp = cases[(mode + (tregion is None)) % 2]
                     ref_like = orc.region_refill(u, mode, check_cube, xform, tregion, like_kind, lp, -np.inf)[1]
                     finite = ref_like[np.isfinite(ref_like)]
                     Lmin = np.median(finite) if len(finite) else 0.0
@@ -259,8 +264,10 @@ def test_device_refill_matches_oracle_chain(ndim, nlive):
                     np.testing.assert_array_equal(got[0], want[0], err_msg=tag)
                     np.testing.assert_array_equal(got[1], want[1], err_msg=tag)
                     assert got[2] == want[2], tag
-                    if mode == 2 and not check_cube:
+                    if mode == 2:
                         assert 0 < want[2][2] < want[2][1] <= want[2][0] < n, (tag, want[2])
+                        if tregion is not None:
+                            assert want[2][1] < want[2][0], (tag, want[2])
 
 
 @pytest.mark.gpu
