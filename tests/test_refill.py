@@ -290,7 +290,7 @@ def test_device_refill_chunked_and_empty():
     assert whole[2][0] == int((whole[0] & 1).sum()) and whole[2][2] == int(((whole[0] & 4) != 0).sum())
     empty = eng.region_refill(np.empty((0, 6)), 2, True, None, None, _native.LOGLIKE_GAUSS, lp, 0.0)
     assert len(empty[0]) == 0 and empty[2] == (0, 0, 0)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(ValueError):
         eng.region_refill(u[:10], 2, True, None, None, _native.LOGLIKE_NONE, None, 0.0)
 
 
