@@ -54,13 +54,17 @@ def build(force=False, verbose=False, extra_flags=()):
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags)
     header_time = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS
                       if os.path.exists(os.path.join(CSRC, h)))
-    objects = []
+    objects, jobs = [], []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         src_time = max(os.path.getmtime(os.path.join(CSRC, src)), header_time)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < src_time:
-            _run([nvcc] + compile_flags + ["-c", "-o", obj, src], verbose)
+            jobs.append([nvcc] + compile_flags + ["-c", "-o", obj, src])
         objects.append(obj)
+    if jobs:   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+            list(pool.map(lambda cmd: _run(cmd, verbose), jobs))
     _run([nvcc, "-shared", "-Xcompiler", "-pthread", "-o", LIBPATH] + objects, verbose)
     return LIBPATH
 

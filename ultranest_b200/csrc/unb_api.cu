@@ -301,6 +301,7 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
     free_live(ctx->scratch_live);
     free_dev(ctx->region.layer_shift); free_dev(ctx->region.layer_mat);
     free_dev(ctx->region.ell_center); free_dev(ctx->region.ell_invcov);
+    free_dev(ctx->region.ell_invcov_pad); free_dev(ctx->region.layer_mat_pad);
     free_dev(ctx->aux0); free_dev(ctx->aux1); free_dev(ctx->aux2); free_dev(ctx->aux3);
     free_dev(ctx->stat); free_dev(ctx->lparams); free_dev(ctx->refill_params);
     free_dev(ctx->boot_rows); free_dev(ctx->boot_u); free_dev(ctx->boot_tiles);
@@ -511,6 +512,19 @@ extern "C" int unb_mean_pair_distance(unb_ctx *ctx, const double *pts, const int
     return UNB_OK;
 }
 
+// zero-padded row-major copy (row stride = ndim rounded up to 8) for the tile prep kernel
+static size_t pad8(size_t d) { return (d + 7) / 8 * 8; }
+static int upload_padded8(unb_ctx *ctx, DevBuf &dst, const double *mat, size_t ndim, cudaStream_t s)
+{
+    const size_t dp = pad8(ndim);
+    std::vector<double> buf(ndim * dp, 0.0);
+    for (size_t r = 0; r < ndim; r++) memcpy(&buf[r * dp], mat + r * ndim, ndim * sizeof(double));
+    UNB_TRY(unb_reserve(ctx, dst, buf.size() * sizeof(double)));
+    UNB_TRY(h2d(ctx, dst.p, buf.data(), buf.size() * sizeof(double), s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));   // buf is a temporary
+    return UNB_OK;
+}
+
 extern "C" int unb_inside_ellipsoid(unb_ctx *ctx, const double *points, size_t m, size_t ndim,
                                     const double *center, const double *invcov,
                                     double square_radius, uint8_t *mask)
@@ -538,6 +552,15 @@ extern "C" int unb_inside_ellipsoid(unb_ctx *ctx, const double *points, size_t m
     p.r2 = square_radius;
     p.mask = (unsigned char *)ln.mask.p;
     p.layer_kind = -1;
+    if (!ctx->exact_only && unb_tile_prep_fits((int)ndim)) {
+        UNB_TRY(upload_padded8(ctx, ctx->aux2, invcov, ndim, s));
+        double fro = 0.0;
+        for (size_t i = 0; i < ndim * ndim; i++) fro += invcov[i] * invcov[i];
+        p.pad_stride = (int)pad8(ndim);
+        p.invcov_pad = (const double *)ctx->aux2.p;
+        p.ell_tol_scale = 2.0 * ((double)(ndim * ndim + 2 * ndim + 8)) * 1.1102230246251565e-16 *
+                          std::sqrt(fro) * (1.0 + 1e-9);
+    }
     UNB_TRY(unb_launch_prep(ctx, p, s));
     UNB_TRY(d2h(ctx, mask, ln.mask.p, m, s));
     UNB_CUDA(ctx, cudaStreamSynchronize(s));
@@ -671,6 +694,8 @@ extern "C" int unb_region_set_layer(unb_ctx *ctx, int kind, const double *shift,
         UNB_TRY(h2d(ctx, R.layer_shift.p, shift, ndim * sizeof(double), s));
         UNB_TRY(h2d(ctx, R.layer_mat.p, mat, mat_n * sizeof(double), s));
         UNB_CUDA(ctx, cudaStreamSynchronize(s));
+        if (kind == UNB_LAYER_AFFINE && unb_tile_prep_fits((int)ndim))
+            UNB_TRY(upload_padded8(ctx, R.layer_mat_pad, mat, ndim, s));
     }
     if (R.layer_kind != kind) R.param_version++;
     R.layer_kind = kind;
@@ -704,6 +729,7 @@ extern "C" int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, cons
     UNB_TRY(h2d(ctx, R.ell_center.p, center, ndim * sizeof(double), s));
     UNB_TRY(h2d(ctx, R.ell_invcov.p, invcov, ndim * ndim * sizeof(double), s));
     UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    if (unb_tile_prep_fits((int)ndim)) UNB_TRY(upload_padded8(ctx, R.ell_invcov_pad, invcov, ndim, s));
     R.ell_d = ndim;
     R.enlarge = enlarge;
     R.have_ellipsoid = true;
@@ -755,6 +781,10 @@ int enqueue_ellipsoid(unb_ctx *ctx, cudaStream_t s, const double *pts_dev, size_
     p.layer_kind = -1;
     p.use_constants = use_const ? 1 : 0;
     p.ell_tol_scale = 2.0 * ((double)(d * d + 2 * d + 8)) * 1.1102230246251565e-16 * R.ell_fro;
+    if (!ctx->exact_only && unb_tile_prep_fits((int)d)) {
+        p.pad_stride = (int)pad8(d);
+        p.invcov_pad = (const double *)R.ell_invcov_pad.p;
+    }
     return unb_launch_prep(ctx, p, s);
 }
 
@@ -776,7 +806,10 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     const bool have32 = R.live.t32_valid && R.live.t32_r2 == R.r2 && ctx->filter_fp32;
     const bool reg_prep = !ctx->exact_only && !idx_dev && R.live.ntiles > 0 && R.live.dr <= 32;
     const bool use_any = reg_prep || (!ctx->exact_only && !idx_dev && have32);
-    const bool fuse_like = reg_prep && like_dev && loglike_kind != UNB_LOGLIKE_NONE;
+    // 32 < d: tile prep kernel (register-blocked products out of shared memory)
+    const bool tile_prep = !ctx->exact_only && unb_tile_prep_fits((int)d);
+    const bool fuse_like = (reg_prep || (tile_prep && use_any)) && like_dev &&
+                           loglike_kind != UNB_LOGLIKE_NONE;
     // ellipsoid parameters through the constant bank whenever they fit (d <= 56)
     const bool const_prep = reg_prep || (!ctx->exact_only && R.live.d <= unb_const_maxd());
     if (const_prep) UNB_TRY(unb_prep_sync_constants(ctx, s));
@@ -797,6 +830,11 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     p.n_items = (int *)ln.counter.p;
     p.use_constants = const_prep ? 1 : 0;
     p.ell_tol_scale = 2.0 * ((double)(d * d + 2 * d + 8)) * 1.1102230246251565e-16 * R.ell_fro;
+    if (tile_prep) {
+        p.pad_stride = (int)pad8(d);
+        p.invcov_pad = (const double *)R.ell_invcov_pad.p;
+        p.mat_pad = (const double *)R.layer_mat_pad.p;
+    }
     if (fuse_like) {
         p.like = like_dev;
         p.loglike_kind = loglike_kind;

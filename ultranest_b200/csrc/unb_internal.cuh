@@ -135,6 +135,8 @@ struct RegionState {
     double enlarge = 0.0;
     double ell_fro = 0.0;     // Frobenius norm of the inverse covariance (ellipsoid filter band)
     DevBuf ell_center, ell_invcov;
+    DevBuf ell_invcov_pad, layer_mat_pad;   // zero-padded copies (row stride pad_stride) for k_prep_tile
+    size_t pad_stride = 0;
     bool have_radius = false;
     double r2 = 0.0;
     long long param_version = 0;   // bumped whenever layer / ellipsoid parameters change
@@ -220,7 +222,12 @@ struct PrepArgs {
     double *like;             // out: fused likelihood of the rows inside the ellipsoid (nullable)
     int loglike_kind;
     const double *lparams;    // device likelihood parameter block
+    // tile kernel (32 < d): zero-padded row-major copies, row stride pad_stride (multiple of 8)
+    int pad_stride;           // 0: tile kernel not requested
+    const double *invcov_pad;
+    const double *mat_pad;
 };
+bool unb_tile_prep_fits(int d);
 int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s);
 size_t unb_const_maxd();
 int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s);

@@ -249,6 +249,185 @@ __global__ void __launch_bounds__(128, UNB_PREP_MINB) k_prep_reg(const PrepArgs 
 }
 
 // ---------------------------------------------------------------------------------------
+// tile variant for 32 < d (rows no longer fit registers): the block's TILE_PTS proposals sit
+// row-major in shared memory (odd stride: a warp's 64-bit reads of one column are conflict
+// free) and the two d x d products -- ellipsoid filter  Y = delta A  and layer transform
+// t = x T -- run as register-blocked products: lane = 4 proposals (lane + 32 i), warp = chunks
+// of 8 matrix columns, so one reduction step is 4 LDS.64 + 4 warp-uniform LDG.128 (matrix row
+// from the zero-padded copy, L1 resident) for 32 independent DFMA.  The reduction index runs
+// ascending in ONE accumulator per output, which is exactly the defined order of the layer
+// transform; the ellipsoid product only feeds the filter, whose band is decided
+// by the reference's einsum order like in k_prep_reg.
+// ---------------------------------------------------------------------------------------
+constexpr int TILE_PTS = 128;
+constexpr int TILE_WARPS = 4;
+
+__device__ __forceinline__ void tile_product(const double *__restrict__ sm, int ds, int lane,
+                                             const double *__restrict__ Mpad, int d, int dp,
+                                             int c0, double (&acc)[4][8])
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[i][c] = 0.0;
+    const double *r0 = sm + (size_t)lane * ds;
+    const double *r1 = r0 + 32 * ds, *r2 = r0 + 64 * ds, *r3 = r0 + 96 * ds;
+    const double2 *mrow = reinterpret_cast<const double2 *>(Mpad + c0);
+    const int mstep = dp >> 1;
+#pragma unroll 2
+    for (int j = 0; j < d; j++, mrow += mstep) {
+        const double2 a01 = __ldg(mrow), a23 = __ldg(mrow + 1), a45 = __ldg(mrow + 2),
+                      a67 = __ldg(mrow + 3);
+        const double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+        const double x[4] = {r0[j], r1[j], r2[j], r3[j]};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) acc[i][c] = fma(x[i], a[c], acc[i][c]);
+    }
+}
+
+// stage  pts[row0 .. row0+TILE_PTS) - shift  into the shared-memory tile (rows >= nvalid: zeros)
+__device__ __forceinline__ void tile_stage(double *sm, int ds, const double *__restrict__ pts,
+                                           long long row0, int nvalid, int d,
+                                           const double *__restrict__ shift)
+{
+    const double *src = pts + row0 * d;
+    const int q = TILE_PTS / d, r = TILE_PTS % d;   // element stride of a thread: TILE_PTS
+    int pt = threadIdx.x / d, k = threadIdx.x % d;
+    const int total = TILE_PTS * d, nv = nvalid * d;
+    for (int e = threadIdx.x; e < total; e += TILE_PTS) {
+        double v = 0.0;
+        if (e < nv) v = __dsub_rn(src[e], shift ? __ldg(shift + k) : 0.0);
+        sm[pt * ds + k] = v;
+        pt += q;
+        k += r;
+        if (k >= d) { k -= d; pt++; }
+    }
+}
+
+__global__ void __launch_bounds__(TILE_PTS) k_prep_tile(const PrepArgs P)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_r[TILE_WARPS][TILE_PTS];
+    __shared__ double s_nd[TILE_WARPS][TILE_PTS];
+    __shared__ int s_pos[TILE_PTS];
+    const int d = P.d, ds = odd_stride(d), dp = P.pad_stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long row0 = (long long)blockIdx.x * TILE_PTS;
+    const long long left = P.m - row0;
+    const int nvalid = left < TILE_PTS ? (int)left : TILE_PTS;
+    const long long j = row0 + tid;
+    const bool valid = tid < nvalid;
+    const int nchunks = dp >> 3;
+    bool inside = valid;
+
+    if (P.center) {
+        tile_stage(sm, ds, P.pts, row0, nvalid, d, P.center);
+        __syncthreads();
+        double rp[4] = {0.0, 0.0, 0.0, 0.0}, ndp[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int ch = warp; ch < nchunks; ch += TILE_WARPS) {
+            const int c0 = ch << 3;
+            double acc[4][8];
+            tile_product(sm, ds, lane, P.invcov_pad, d, dp, c0, acc);
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (c0 + c < d) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const double dc = sm[(size_t)(lane + 32 * i) * ds + c0 + c];
+                        rp[i] = fma(acc[i][c], dc, rp[i]);
+                        ndp[i] = fma(dc, dc, ndp[i]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            s_r[warp][lane + 32 * i] = rp[i];
+            s_nd[warp][lane + 32 * i] = ndp[i];
+        }
+        __syncthreads();
+        double rfast = 0.0, nd = 0.0;
+#pragma unroll
+        for (int w = 0; w < TILE_WARPS; w++) {
+            rfast = __dadd_rn(rfast, s_r[w][tid]);
+            nd = __dadd_rn(nd, s_nd[w][tid]);
+        }
+        // same band argument as k_prep_reg: any summation order of the d^2 products (fused or
+        // not) stays within (d^2+2d+4) u |delta|^2 ||A||_F of delta^T A delta; tol is 2x that
+        const double tol = __dmul_rn(P.ell_tol_scale, nd);
+        bool in = rfast <= P.r2;
+        const bool band = !(fabs(__dsub_rn(rfast, P.r2)) > tol);   // also true for NaN
+        if (band && valid) {
+            const double *my = sm + (size_t)tid * ds;
+            double acc = 0.0;
+            for (int jj = 0; jj < d; jj++) {
+                const double dj = my[jj];
+                const double *Arow = P.invcov + (size_t)jj * d;
+                for (int k = 0; k < d; k++)
+                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
+            }
+            in = acc <= P.r2;
+        }
+        inside = valid && in;
+        if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
+    }
+
+    int nsurv = 0;
+    if (P.layer_kind >= 0) {
+        const unsigned ball = __ballot_sync(FULL, inside);
+        int base = 0;
+        if (lane == 0 && ball) base = atomicAdd(P.n_items, __popc(ball));
+        base = __shfl_sync(FULL, base, 0);
+        const int pos = inside ? base + __popc(ball & ((1u << lane) - 1)) : -1;
+        s_pos[tid] = pos;
+        if (inside) P.items[pos] = (int)j;
+        nsurv = __syncthreads_count(inside);   // also: every warp is done with the delta tile
+        if (nsurv) {
+            if (P.layer_kind == UNB_LAYER_AFFINE) {
+                tile_stage(sm, ds, P.pts, row0, nvalid, d, P.shift);
+                __syncthreads();
+                for (int ch = warp; ch < nchunks; ch += TILE_WARPS) {
+                    const int c0 = ch << 3;
+                    double acc[4][8];
+                    tile_product(sm, ds, lane, P.mat_pad, d, dp, c0, acc);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int pos_i = s_pos[lane + 32 * i];
+                        if (pos_i < 0) continue;
+                        double *out = P.tcand + (size_t)pos_i * d + c0;
+#pragma unroll
+                        for (int c = 0; c < 8; c++)
+                            if (c0 + c < d) out[c] = acc[i][c];
+                    }
+                }
+            } else {
+                const double *src = P.pts + row0 * d;
+                const int nv = nvalid * d;
+                for (int e = tid; e < nv; e += TILE_PTS) {
+                    const int pt = e / d, k = e - pt * d;
+                    const int pos_e = s_pos[pt];
+                    if (pos_e < 0) continue;
+                    double v = src[e];
+                    if (P.layer_kind == UNB_LAYER_SCALING)
+                        v = __ddiv_rn(__dsub_rn(v, __ldg(P.shift + k)), __ldg(P.mat + k));
+                    P.tcand[(size_t)pos_e * d + k] = v;
+                }
+            }
+        }
+    }
+    if (P.like) {
+        __syncthreads();   // the tile becomes per-thread scratch of the likelihood
+        if (valid) {
+            double like = -__longlong_as_double(0x7ff0000000000000LL);
+            if (inside) like = loglike_row(P.loglike_kind, P.pts + j * d, d, sm + (size_t)tid * ds, P.lparams);
+            P.like[j] = like;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // layer transforms
 // ---------------------------------------------------------------------------------------
 __global__ void k_transform(int kind, int inverse, const double *__restrict__ in, long long m,
@@ -542,6 +721,12 @@ int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, c
 
 size_t unb_const_maxd() { return CONST_MAXD; }
 
+// the tile prep kernel serves 32 < d as long as its 128-row tile fits shared memory
+bool unb_tile_prep_fits(int d)
+{
+    return d > PREP_MAXD && (size_t)TILE_PTS * odd_stride(d) * sizeof(double) <= ROW_SMEM_BUDGET;
+}
+
 size_t unb_max_rowwise_d() { return ROW_SMEM_BUDGET / sizeof(double) / 32 - 1; }
 
 // -- __constant__ parameter block of the register prep kernel -------------------------------
@@ -617,6 +802,19 @@ int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s)
         case 32: return launch_prep_reg<32>(ctx, p, s);
         default: break;
         }
+    }
+    if (p.pad_stride > 0 && unb_tile_prep_fits(p.d)) {
+        if ((p.center && !p.invcov_pad) || (p.layer_kind == UNB_LAYER_AFFINE && !p.mat_pad) ||
+            p.pad_stride % 8 != 0 || p.pad_stride < p.d)
+            return unb_fail(ctx, UNB_ERR_ARG, "tile prep kernel needs the padded matrices");
+        const size_t smem = (size_t)TILE_PTS * odd_stride(p.d) * sizeof(double);
+        // static + dynamic shared memory can pass 48 KB before the dynamic part alone does
+        UNB_CUDA(ctx, cudaFuncSetAttribute(k_prep_tile, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)ROW_SMEM_BUDGET));
+        k_prep_tile<<<(unsigned)((p.m + TILE_PTS - 1) / TILE_PTS), TILE_PTS, smem, s>>>(p);
+        ctx->launches++;
+        UNB_CUDA(ctx, cudaGetLastError());
+        return UNB_OK;
     }
     const int threads = row_threads(p.d);
     if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%d too large for the row kernels", p.d);
