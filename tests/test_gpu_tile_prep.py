@@ -9,7 +9,7 @@ from oracle import cport
 
 pytestmark = pytest.mark.gpu
 
-DIMS = [33, 40, 50, 64, 65, 100, 128, 190]
+DIMS = [33, 40, 50, 64, 65, 100, 128, 140, 190]   # 190: beyond the tile kernel, plain row kernel
 
 
 @pytest.fixture(scope="module")

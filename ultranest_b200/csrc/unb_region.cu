@@ -253,31 +253,47 @@ __global__ void __launch_bounds__(128, UNB_PREP_MINB) k_prep_reg(const PrepArgs 
 // row-major in shared memory (odd stride: a warp's 64-bit reads of one column are conflict
 // free) and the two d x d products -- ellipsoid filter  Y = delta A  and layer transform
 // t = x T -- run as register-blocked products: lane = 4 proposals (lane + 32 i), warp = chunks
-// of 8 matrix columns, so one reduction step is 4 LDS.64 + 4 warp-uniform LDG.128 (matrix row
-// from the zero-padded copy, L1 resident) for 32 independent DFMA.  The reduction index runs
-// ascending in ONE accumulator per output, which is exactly the defined order of the layer
-// transform; the ellipsoid product only feeds the filter, whose band is decided
-// by the reference's einsum order like in k_prep_reg.
+// of 8 matrix columns.  The warp first copies its d x 8 matrix panel (zero-padded copy, 128-bit
+// coalesced loads, all in flight together) into its own shared-memory slot, so one reduction
+// step is 4 LDS.64 + 4 broadcast LDS.128 for 32 independent DFMA and never waits on L2.
+// The reduction index runs ascending in ONE accumulator per output, which is exactly the
+// defined order of the layer transform; the ellipsoid product only feeds the
+// filter, whose band is decided by the reference's einsum order like in k_prep_reg.
 // ---------------------------------------------------------------------------------------
 constexpr int TILE_PTS = 128;
-constexpr int TILE_WARPS = 4;
+constexpr int TILE_WARPS = 8;
+constexpr int TILE_THREADS = TILE_WARPS * 32;
+constexpr size_t TILE_SMEM_BUDGET = 216 * 1024;
+
+__host__ __device__ inline size_t tile_smem_doubles(int d)
+{
+    return (size_t)TILE_PTS * odd_stride(d) + (size_t)TILE_WARPS * d * 8;
+}
 
 __device__ __forceinline__ void tile_product(const double *__restrict__ sm, int ds, int lane,
+                                             double *__restrict__ panel,
                                              const double *__restrict__ Mpad, int d, int dp,
                                              int c0, double (&acc)[4][8])
 {
+    // panel[j][0..8) = Mpad[j][c0 .. c0+8)
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(Mpad + c0);
+        double2 *dst = reinterpret_cast<double2 *>(panel);
+        const int units = d * 4, hstep = dp >> 1;
+        __syncwarp();   // the previous chunk's reads of the slot are done
+        for (int u = lane; u < units; u += 32) dst[u] = __ldg(src + (size_t)(u >> 2) * hstep + (u & 3));
+        __syncwarp();
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[i][c] = 0.0;
     const double *r0 = sm + (size_t)lane * ds;
     const double *r1 = r0 + 32 * ds, *r2 = r0 + 64 * ds, *r3 = r0 + 96 * ds;
-    const double2 *mrow = reinterpret_cast<const double2 *>(Mpad + c0);
-    const int mstep = dp >> 1;
+    const double2 *prow = reinterpret_cast<const double2 *>(panel);
 #pragma unroll 2
-    for (int j = 0; j < d; j++, mrow += mstep) {
-        const double2 a01 = __ldg(mrow), a23 = __ldg(mrow + 1), a45 = __ldg(mrow + 2),
-                      a67 = __ldg(mrow + 3);
+    for (int j = 0; j < d; j++, prow += 4) {
+        const double2 a01 = prow[0], a23 = prow[1], a45 = prow[2], a67 = prow[3];
         const double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
         const double x[4] = {r0[j], r1[j], r2[j], r3[j]};
 #pragma unroll
@@ -293,10 +309,11 @@ __device__ __forceinline__ void tile_stage(double *sm, int ds, const double *__r
                                            const double *__restrict__ shift)
 {
     const double *src = pts + row0 * d;
-    const int q = TILE_PTS / d, r = TILE_PTS % d;   // element stride of a thread: TILE_PTS
+    const int q = TILE_THREADS / d, r = TILE_THREADS % d;   // a thread strides TILE_THREADS elements
     int pt = threadIdx.x / d, k = threadIdx.x % d;
     const int total = TILE_PTS * d, nv = nvalid * d;
-    for (int e = threadIdx.x; e < total; e += TILE_PTS) {
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += TILE_THREADS) {
         double v = 0.0;
         if (e < nv) v = __dsub_rn(src[e], shift ? __ldg(shift + k) : 0.0);
         sm[pt * ds + k] = v;
@@ -306,19 +323,20 @@ __device__ __forceinline__ void tile_stage(double *sm, int ds, const double *__r
     }
 }
 
-__global__ void __launch_bounds__(TILE_PTS) k_prep_tile(const PrepArgs P)
+__global__ void __launch_bounds__(TILE_THREADS) k_prep_tile(const PrepArgs P)
 {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double s_r[TILE_WARPS][TILE_PTS];
-    __shared__ double s_nd[TILE_WARPS][TILE_PTS];
     __shared__ int s_pos[TILE_PTS];
     const int d = P.d, ds = odd_stride(d), dp = P.pad_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // per-warp matrix panel slots behind the tile (16-byte aligned: even offset)
+    double *panels = sm + (((size_t)TILE_PTS * ds + 1) & ~(size_t)1);
+    double *panel = panels + (size_t)warp * d * 8;
     const long long row0 = (long long)blockIdx.x * TILE_PTS;
     const long long left = P.m - row0;
     const int nvalid = left < TILE_PTS ? (int)left : TILE_PTS;
     const long long j = row0 + tid;
-    const bool valid = tid < nvalid;
+    const bool valid = tid < nvalid;   // threads >= TILE_PTS own no proposal
     const int nchunks = dp >> 3;
     bool inside = valid;
 
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(TILE_PTS) k_prep_tile(const PrepArgs P)
         for (int ch = warp; ch < nchunks; ch += TILE_WARPS) {
             const int c0 = ch << 3;
             double acc[4][8];
-            tile_product(sm, ds, lane, P.invcov_pad, d, dp, c0, acc);
+            tile_product(sm, ds, lane, panel, P.invcov_pad, d, dp, c0, acc);
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 if (c0 + c < d) {
@@ -342,48 +360,52 @@ __global__ void __launch_bounds__(TILE_PTS) k_prep_tile(const PrepArgs P)
                 }
             }
         }
+        // the warp's partial sums go through its own panel slot (d*8 >= 2*TILE_PTS doubles)
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            s_r[warp][lane + 32 * i] = rp[i];
-            s_nd[warp][lane + 32 * i] = ndp[i];
+            panel[lane + 32 * i] = rp[i];
+            panel[TILE_PTS + lane + 32 * i] = ndp[i];
         }
         __syncthreads();
-        double rfast = 0.0, nd = 0.0;
+        if (tid < TILE_PTS) {
+            double rfast = 0.0, nd = 0.0;
 #pragma unroll
-        for (int w = 0; w < TILE_WARPS; w++) {
-            rfast = __dadd_rn(rfast, s_r[w][tid]);
-            nd = __dadd_rn(nd, s_nd[w][tid]);
-        }
-        // same band argument as k_prep_reg: any summation order of the d^2 products (fused or
-        // not) stays within (d^2+2d+4) u |delta|^2 ||A||_F of delta^T A delta; tol is 2x that
-        const double tol = __dmul_rn(P.ell_tol_scale, nd);
-        bool in = rfast <= P.r2;
-        const bool band = !(fabs(__dsub_rn(rfast, P.r2)) > tol);   // also true for NaN
-        if (band && valid) {
-            const double *my = sm + (size_t)tid * ds;
-            double acc = 0.0;
-            for (int jj = 0; jj < d; jj++) {
-                const double dj = my[jj];
-                const double *Arow = P.invcov + (size_t)jj * d;
-                for (int k = 0; k < d; k++)
-                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
+            for (int w = 0; w < TILE_WARPS; w++) {
+                rfast = __dadd_rn(rfast, panels[(size_t)w * d * 8 + tid]);
+                nd = __dadd_rn(nd, panels[(size_t)w * d * 8 + TILE_PTS + tid]);
             }
-            in = acc <= P.r2;
+            // same band argument as k_prep_reg: any summation order of the d^2 products (fused
+            // or not) stays within (d^2+2d+4) u |delta|^2 ||A||_F of delta^T A delta; tol is 2x that
+            const double tol = __dmul_rn(P.ell_tol_scale, nd);
+            bool in = rfast <= P.r2;
+            const bool band = !(fabs(__dsub_rn(rfast, P.r2)) > tol);   // also true for NaN
+            if (band && valid) {
+                const double *my = sm + (size_t)tid * ds;
+                double acc = 0.0;
+                for (int jj = 0; jj < d; jj++) {
+                    const double dj = my[jj];
+                    const double *Arow = P.invcov + (size_t)jj * d;
+                    for (int k = 0; k < d; k++)
+                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
+                }
+                in = acc <= P.r2;
+            }
+            inside = valid && in;
+            if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
         }
-        inside = valid && in;
-        if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
     }
 
-    int nsurv = 0;
     if (P.layer_kind >= 0) {
         const unsigned ball = __ballot_sync(FULL, inside);
         int base = 0;
         if (lane == 0 && ball) base = atomicAdd(P.n_items, __popc(ball));
         base = __shfl_sync(FULL, base, 0);
         const int pos = inside ? base + __popc(ball & ((1u << lane) - 1)) : -1;
-        s_pos[tid] = pos;
+        if (tid < TILE_PTS) s_pos[tid] = pos;
         if (inside) P.items[pos] = (int)j;
-        nsurv = __syncthreads_count(inside);   // also: every warp is done with the delta tile
+        // barrier: s_pos visible, every warp done with the delta tile and the panel slots
+        const int nsurv = __syncthreads_count(inside);
         if (nsurv) {
             if (P.layer_kind == UNB_LAYER_AFFINE) {
                 tile_stage(sm, ds, P.pts, row0, nvalid, d, P.shift);
@@ -391,7 +413,7 @@ __global__ void __launch_bounds__(TILE_PTS) k_prep_tile(const PrepArgs P)
                 for (int ch = warp; ch < nchunks; ch += TILE_WARPS) {
                     const int c0 = ch << 3;
                     double acc[4][8];
-                    tile_product(sm, ds, lane, P.mat_pad, d, dp, c0, acc);
+                    tile_product(sm, ds, lane, panel, P.mat_pad, d, dp, c0, acc);
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int pos_i = s_pos[lane + 32 * i];
@@ -405,7 +427,7 @@ __global__ void __launch_bounds__(TILE_PTS) k_prep_tile(const PrepArgs P)
             } else {
                 const double *src = P.pts + row0 * d;
                 const int nv = nvalid * d;
-                for (int e = tid; e < nv; e += TILE_PTS) {
+                for (int e = tid; e < nv; e += TILE_THREADS) {
                     const int pt = e / d, k = e - pt * d;
                     const int pos_e = s_pos[pt];
                     if (pos_e < 0) continue;
@@ -724,7 +746,7 @@ size_t unb_const_maxd() { return CONST_MAXD; }
 // the tile prep kernel serves 32 < d as long as its 128-row tile fits shared memory
 bool unb_tile_prep_fits(int d)
 {
-    return d > PREP_MAXD && (size_t)TILE_PTS * odd_stride(d) * sizeof(double) <= ROW_SMEM_BUDGET;
+    return d > PREP_MAXD && tile_smem_doubles(d) * sizeof(double) <= TILE_SMEM_BUDGET;
 }
 
 size_t unb_max_rowwise_d() { return ROW_SMEM_BUDGET / sizeof(double) / 32 - 1; }
@@ -807,11 +829,10 @@ int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s)
         if ((p.center && !p.invcov_pad) || (p.layer_kind == UNB_LAYER_AFFINE && !p.mat_pad) ||
             p.pad_stride % 8 != 0 || p.pad_stride < p.d)
             return unb_fail(ctx, UNB_ERR_ARG, "tile prep kernel needs the padded matrices");
-        const size_t smem = (size_t)TILE_PTS * odd_stride(p.d) * sizeof(double);
-        // static + dynamic shared memory can pass 48 KB before the dynamic part alone does
+        const size_t smem = (tile_smem_doubles(p.d) + 2) * sizeof(double);
         UNB_CUDA(ctx, cudaFuncSetAttribute(k_prep_tile, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)ROW_SMEM_BUDGET));
-        k_prep_tile<<<(unsigned)((p.m + TILE_PTS - 1) / TILE_PTS), TILE_PTS, smem, s>>>(p);
+                                           (int)(TILE_SMEM_BUDGET + 1024)));
+        k_prep_tile<<<(unsigned)((p.m + TILE_PTS - 1) / TILE_PTS), TILE_THREADS, smem, s>>>(p);
         ctx->launches++;
         UNB_CUDA(ctx, cudaGetLastError());
         return UNB_OK;
