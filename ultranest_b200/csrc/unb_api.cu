@@ -514,11 +514,20 @@ extern "C" int unb_mean_pair_distance(unb_ctx *ctx, const double *pts, const int
 
 // zero-padded row-major copy (row stride = ndim rounded up to 8) for the tile prep kernel
 static size_t pad8(size_t d) { return (d + 7) / 8 * 8; }
-static int upload_padded8(unb_ctx *ctx, DevBuf &dst, const double *mat, size_t ndim, cudaStream_t s)
+static int upload_padded8(unb_ctx *ctx, DevBuf &dst, const double *mat, size_t ndim, cudaStream_t s,
+                          bool fold = false)
 {
     const size_t dp = pad8(ndim);
     std::vector<double> buf(ndim * dp, 0.0);
-    for (size_t r = 0; r < ndim; r++) memcpy(&buf[r * dp], mat + r * ndim, ndim * sizeof(double));
+    for (size_t r = 0; r < ndim; r++) {
+        if (!fold) {
+            memcpy(&buf[r * dp], mat + r * ndim, ndim * sizeof(double));
+            continue;
+        }
+        // quadratic form folded onto the upper triangle (the ellipsoid filter of k_prep_tile)
+        buf[r * dp + r] = mat[r * ndim + r];
+        for (size_t c = r + 1; c < ndim; c++) buf[r * dp + c] = mat[r * ndim + c] + mat[c * ndim + r];
+    }
     UNB_TRY(unb_reserve(ctx, dst, buf.size() * sizeof(double)));
     UNB_TRY(h2d(ctx, dst.p, buf.data(), buf.size() * sizeof(double), s));
     UNB_CUDA(ctx, cudaStreamSynchronize(s));   // buf is a temporary
@@ -553,7 +562,7 @@ extern "C" int unb_inside_ellipsoid(unb_ctx *ctx, const double *points, size_t m
     p.mask = (unsigned char *)ln.mask.p;
     p.layer_kind = -1;
     if (!ctx->exact_only && unb_tile_prep_fits((int)ndim)) {
-        UNB_TRY(upload_padded8(ctx, ctx->aux2, invcov, ndim, s));
+        UNB_TRY(upload_padded8(ctx, ctx->aux2, invcov, ndim, s, true));
         double fro = 0.0;
         for (size_t i = 0; i < ndim * ndim; i++) fro += invcov[i] * invcov[i];
         p.pad_stride = (int)pad8(ndim);
@@ -729,7 +738,7 @@ extern "C" int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, cons
     UNB_TRY(h2d(ctx, R.ell_center.p, center, ndim * sizeof(double), s));
     UNB_TRY(h2d(ctx, R.ell_invcov.p, invcov, ndim * ndim * sizeof(double), s));
     UNB_CUDA(ctx, cudaStreamSynchronize(s));
-    if (unb_tile_prep_fits((int)ndim)) UNB_TRY(upload_padded8(ctx, R.ell_invcov_pad, invcov, ndim, s));
+    if (unb_tile_prep_fits((int)ndim)) UNB_TRY(upload_padded8(ctx, R.ell_invcov_pad, invcov, ndim, s, true));
     R.ell_d = ndim;
     R.enlarge = enlarge;
     R.have_ellipsoid = true;

@@ -224,7 +224,7 @@ struct PrepArgs {
     const double *lparams;    // device likelihood parameter block
     // tile kernel (32 < d): zero-padded row-major copies, row stride pad_stride (multiple of 8)
     int pad_stride;           // 0: tile kernel not requested
-    const double *invcov_pad;
+    const double *invcov_pad;   // FOLDED inverse covariance: A_jj on, A_jc + A_cj above, 0 below the diagonal
     const double *mat_pad;
 };
 bool unb_tile_prep_fits(int d);

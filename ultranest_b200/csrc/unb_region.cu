@@ -256,9 +256,10 @@ __global__ void __launch_bounds__(128, UNB_PREP_MINB) k_prep_reg(const PrepArgs 
 // of 8 matrix columns.  The warp first copies its d x 8 matrix panel (zero-padded copy, 128-bit
 // coalesced loads, all in flight together) into its own shared-memory slot, so one reduction
 // step is 4 LDS.64 + 4 broadcast LDS.128 for 32 independent DFMA and never waits on L2.
-// The reduction index runs ascending in ONE accumulator per output, which is exactly the
-// defined order of the layer transform; the ellipsoid product only feeds the
-// filter, whose band is decided by the reference's einsum order like in k_prep_reg.
+// In the layer transform the reduction index runs ascending in ONE accumulator per output,
+// which is exactly its defined order; the ellipsoid product only feeds the
+// filter (band decided by the reference's einsum order, like in k_prep_reg), so it is free to
+// use the folded upper-triangular matrix -- half the multiply-adds.
 // ---------------------------------------------------------------------------------------
 constexpr int TILE_PTS = 128;
 constexpr int TILE_WARPS = 8;
@@ -272,14 +273,14 @@ __host__ __device__ inline size_t tile_smem_doubles(int d)
 
 __device__ __forceinline__ void tile_product(const double *__restrict__ sm, int ds, int lane,
                                              double *__restrict__ panel,
-                                             const double *__restrict__ Mpad, int d, int dp,
-                                             int c0, double (&acc)[4][8])
+                                             const double *__restrict__ Mpad, int ja, int jb,
+                                             int dp, int c0, double (&acc)[4][8])
 {
-    // panel[j][0..8) = Mpad[j][c0 .. c0+8)
+    // panel[j - ja][0..8) = Mpad[j][c0 .. c0+8),  ja <= j < jb
     {
-        const double2 *src = reinterpret_cast<const double2 *>(Mpad + c0);
+        const double2 *src = reinterpret_cast<const double2 *>(Mpad + (size_t)ja * dp + c0);
         double2 *dst = reinterpret_cast<double2 *>(panel);
-        const int units = d * 4, hstep = dp >> 1;
+        const int units = (jb - ja) * 4, hstep = dp >> 1;
         __syncwarp();   // the previous chunk's reads of the slot are done
         for (int u = lane; u < units; u += 32) dst[u] = __ldg(src + (size_t)(u >> 2) * hstep + (u & 3));
         __syncwarp();
@@ -292,7 +293,7 @@ __device__ __forceinline__ void tile_product(const double *__restrict__ sm, int 
     const double *r1 = r0 + 32 * ds, *r2 = r0 + 64 * ds, *r3 = r0 + 96 * ds;
     const double2 *prow = reinterpret_cast<const double2 *>(panel);
 #pragma unroll 2
-    for (int j = 0; j < d; j++, prow += 4) {
+    for (int j = ja; j < jb; j++, prow += 4) {
         const double2 a01 = prow[0], a23 = prow[1], a45 = prow[2], a67 = prow[3];
         const double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
         const double x[4] = {r0[j], r1[j], r2[j], r3[j]};
@@ -303,23 +304,41 @@ __device__ __forceinline__ void tile_product(const double *__restrict__ sm, int 
     }
 }
 
-// stage  pts[row0 .. row0+TILE_PTS) - shift  into the shared-memory tile (rows >= nvalid: zeros)
+// stage  pts[row0 .. row0+TILE_PTS) - shift  into the shared-memory tile (rows >= nvalid: zeros).
+// The raw rows travel global -> shared memory as 8-byte cp.async copies (LDGSTS: no register
+// staging, every copy of the thread in flight at once); the thread then subtracts the shift from
+// exactly the elements it copied, so only its own cp.async group has to be waited for.
 __device__ __forceinline__ void tile_stage(double *sm, int ds, const double *__restrict__ pts,
                                            long long row0, int nvalid, int d,
                                            const double *__restrict__ shift)
 {
     const double *src = pts + row0 * d;
     const int q = TILE_THREADS / d, r = TILE_THREADS % d;   // a thread strides TILE_THREADS elements
-    int pt = threadIdx.x / d, k = threadIdx.x % d;
+    const int pt0 = threadIdx.x / d, k0 = threadIdx.x % d;
     const int total = TILE_PTS * d, nv = nvalid * d;
-#pragma unroll 4
+    int pt = pt0, k = k0;
     for (int e = threadIdx.x; e < total; e += TILE_THREADS) {
-        double v = 0.0;
-        if (e < nv) v = __dsub_rn(src[e], shift ? __ldg(shift + k) : 0.0);
-        sm[pt * ds + k] = v;
+        double *dst = sm + pt * ds + k;
+        if (e < nv)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src + e)
+                         : "memory");
+        else
+            *dst = 0.0;
         pt += q;
         k += r;
         if (k >= d) { k -= d; pt++; }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (shift) {
+        pt = pt0;
+        k = k0;
+        for (int e = threadIdx.x; e < nv; e += TILE_THREADS) {
+            double *dst = sm + pt * ds + k;
+            *dst = __dsub_rn(*dst, __ldg(shift + k));
+            pt += q;
+            k += r;
+            if (k >= d) { k -= d; pt++; }
+        }
     }
 }
 
@@ -343,45 +362,53 @@ __global__ void __launch_bounds__(TILE_THREADS) k_prep_tile(const PrepArgs P)
     if (P.center) {
         tile_stage(sm, ds, P.pts, row0, nvalid, d, P.center);
         __syncthreads();
-        double rp[4] = {0.0, 0.0, 0.0, 0.0}, ndp[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int ch = warp; ch < nchunks; ch += TILE_WARPS) {
-            const int c0 = ch << 3;
-            double acc[4][8];
-            tile_product(sm, ds, lane, panel, P.invcov_pad, d, dp, c0, acc);
+        // delta^T A delta = sum over j <= c of delta_j S_jc delta_c with S the folded matrix
+        // (S_jj = A_jj, S_jc = A_jc + A_cj for j < c, 0 below the diagonal): chunk ch only
+        // needs the rows j < 8 ch + 8.  The rows of all chunks, laid end to end, are cut into
+        // TILE_WARPS equal segments -- any partition of the (j, c) products sums to the same
+        // filter value -- so the warps carry equal work whatever d is.
+        double rp[4] = {0.0, 0.0, 0.0, 0.0};
+        {
+            int total_rows = 0;
+            for (int ch = 0; ch < nchunks; ch++) total_rows += min(8 * ch + 8, d);
+            const int lo = (int)((long long)total_rows * warp / TILE_WARPS);
+            const int hi = (int)((long long)total_rows * (warp + 1) / TILE_WARPS);
+            int prefix = 0;
+            for (int ch = 0; ch < nchunks && prefix < hi; ch++) {
+                const int rows = min(8 * ch + 8, d);
+                const int ja = max(lo - prefix, 0), jb = min(hi - prefix, rows);
+                prefix += rows;
+                if (ja >= jb) continue;
+                const int c0 = ch << 3;
+                double acc[4][8];
+                tile_product(sm, ds, lane, panel, P.invcov_pad, ja, jb, dp, c0, acc);
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                if (c0 + c < d) {
+                for (int c = 0; c < 8; c++) {
+                    if (c0 + c < d) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const double dc = sm[(size_t)(lane + 32 * i) * ds + c0 + c];
-                        rp[i] = fma(acc[i][c], dc, rp[i]);
-                        ndp[i] = fma(dc, dc, ndp[i]);
+                        for (int i = 0; i < 4; i++)
+                            rp[i] = fma(acc[i][c], sm[(size_t)(lane + 32 * i) * ds + c0 + c], rp[i]);
                     }
                 }
             }
         }
-        // the warp's partial sums go through its own panel slot (d*8 >= 2*TILE_PTS doubles)
+        // the warp's partial sums go through its own panel slot (d*8 >= TILE_PTS doubles)
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            panel[lane + 32 * i] = rp[i];
-            panel[TILE_PTS + lane + 32 * i] = ndp[i];
-        }
+        for (int i = 0; i < 4; i++) panel[lane + 32 * i] = rp[i];
         __syncthreads();
         if (tid < TILE_PTS) {
+            const double *my = sm + (size_t)tid * ds;
             double rfast = 0.0, nd = 0.0;
 #pragma unroll
-            for (int w = 0; w < TILE_WARPS; w++) {
-                rfast = __dadd_rn(rfast, panels[(size_t)w * d * 8 + tid]);
-                nd = __dadd_rn(nd, panels[(size_t)w * d * 8 + TILE_PTS + tid]);
-            }
+            for (int w = 0; w < TILE_WARPS; w++) rfast = __dadd_rn(rfast, panels[(size_t)w * d * 8 + tid]);
+            for (int k = 0; k < d; k++) nd = fma(my[k], my[k], nd);
             // same band argument as k_prep_reg: any summation order of the d^2 products (fused
             // or not) stays within (d^2+2d+4) u |delta|^2 ||A||_F of delta^T A delta; tol is 2x that
             const double tol = __dmul_rn(P.ell_tol_scale, nd);
             bool in = rfast <= P.r2;
             const bool band = !(fabs(__dsub_rn(rfast, P.r2)) > tol);   // also true for NaN
             if (band && valid) {
-                const double *my = sm + (size_t)tid * ds;
                 double acc = 0.0;
                 for (int jj = 0; jj < d; jj++) {
                     const double dj = my[jj];
@@ -413,7 +440,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_prep_tile(const PrepArgs P)
                 for (int ch = warp; ch < nchunks; ch += TILE_WARPS) {
                     const int c0 = ch << 3;
                     double acc[4][8];
-                    tile_product(sm, ds, lane, panel, P.mat_pad, d, dp, c0, acc);
+                    tile_product(sm, ds, lane, panel, P.mat_pad, 0, d, dp, c0, acc);
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int pos_i = s_pos[lane + 32 * i];
