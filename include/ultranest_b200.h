@@ -265,6 +265,78 @@ int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t ndim,
                       const unb_refill_desc *desc, uint8_t *flags, double *like,
                       int64_t *counts);
 
+/* ------------------------------------------------ population step-sampler helpers
+ * (SURVEY 8-f rank 2): ultranest/stepfuncs.pyx, the compiled helpers of the vectorised slice
+ * samplers in ultranest/popstepsampler.py.  Boolean arrays are NumPy bool (1 byte), integer
+ * arrays int64 (stepfuncs.pyx:16-17).  Arrays the reference updates in place are in/out here.
+ * Random draws are made by the host (np.random, reference order) and passed in as arrays. */
+
+/* within_unit_cube(u), stepfuncs.pyx:22-52: acceptable[i] = all(0 < u[i,:] < 1). */
+int unb_within_unit_cube(unb_ctx *ctx, const double *u, size_t n, size_t ndim, uint8_t *acceptable);
+
+/* evolve_prepare(searching_left, searching_right), stepfuncs.pyx:57-94. */
+int unb_evolve_prepare(unb_ctx *ctx, const uint8_t *searching_left, const uint8_t *searching_right,
+                       size_t n, uint8_t *search_right, uint8_t *bisecting);
+
+/* evolve_update(...), stepfuncs.pyx:99-183.  Lnew[n_lnew]: one value per acceptable walker in
+ * walker order; currentt, current_left, current_right, searching_left, searching_right and
+ * success are updated in place. */
+int unb_evolve_update(unb_ctx *ctx, const uint8_t *acceptable, const double *Lnew, size_t n_lnew,
+                      double Lmin, const uint8_t *search_right, const uint8_t *bisecting,
+                      double *currentt, double *current_left, double *current_right,
+                      uint8_t *searching_left, uint8_t *searching_right, uint8_t *success, size_t n);
+
+/* Built-in prior transform + likelihood evaluated inside the fused step kernels
+ * (UNB_XFORM_*, UNB_LOGLIKE_*; parameters as for unb_refill_desc). */
+typedef struct unb_step_desc {
+    int32_t xform_kind;
+    int32_t loglike_kind;
+    const double *xform_scale;  /* [ndim] (SCALE_SHIFT) */
+    const double *xform_lo;     /* [ndim] */
+    const double *lparams;      /* GAUSS: centers[ndim], sigma, norm_const */
+} unb_step_desc;
+
+/* evolve(transform, loglike, Lmin, ...), stepfuncs.pyx:189-282, as ONE kernel for a device
+ * transform + likelihood: proposal on the slice (currentu is overwritten by the proposals, the
+ * reference's `unew = currentu` alias, :252), unit-cube test, v = transform(u), L = loglike(v),
+ * slice-state update.  currentt of the bisecting walkers must already hold the uniform draws
+ * of :255.  Out: acceptable[n] (nc = its sum), success[n], like[n] (-inf where not acceptable). */
+int unb_evolve(unb_ctx *ctx, const unb_step_desc *desc, double Lmin, double *currentu,
+               const double *currentv, double *currentt, double *current_left,
+               double *current_right, uint8_t *searching_left, uint8_t *searching_right, size_t n,
+               size_t ndim, uint8_t *acceptable, uint8_t *success, double *like);
+
+/* step_back(Lmin, allL, generation, currentt), stepfuncs.pyx:285-334; allL is
+ * (nwalkers x ncols) row-major, ncols <= 2048.  In place. */
+int unb_step_back(unb_ctx *ctx, double Lmin, double *allL, size_t nwalkers, size_t ncols,
+                  int64_t *generation, double *currentt);
+
+/* update_vectorised_slice_sampler(...), stepfuncs.pyx:537-630.  In place on tleft, tright,
+ * worker_running, status, allu, allL, allp; *discarded = the returned count. */
+int unb_update_vectorised_slice_sampler(
+    unb_ctx *ctx, const double *t, double *tleft, double *tright, const double *proposed_L,
+    const double *proposed_u, const double *proposed_p, int64_t *worker_running, int64_t *status,
+    double likelihood_threshold, double shrink_factor, double *allu, double *allL, double *allp,
+    size_t popsize, size_t ndim, size_t nparams, int64_t *discarded);
+
+/* Inner loop of PopulationSimpleSliceSampler.__next__ (popstepsampler.py:916-965) with the
+ * population resident on the device:
+ *   begin   : upload allu, allL, v and the slice limits; allp = NaN, worker_running = arange,
+ *             status = 0 (popstepsampler.py:908, 932-934);
+ *   iterate : one pass -- t from the uniform draws (:942-943), proposals (:945-947), device
+ *             transform + likelihood (:949-950), update_vectorised_slice_sampler (:954-957);
+ *             returns the number of points still running and the discarded evaluations;
+ *   end     : download the state (any pointer may be NULL).
+ * Any other step-helper call on the same context ends the session. */
+int unb_popslice_begin(unb_ctx *ctx, const unb_step_desc *desc, const double *allu,
+                       const double *allL, const double *v, const double *tleft,
+                       const double *tright, size_t popsize, size_t ndim,
+                       double likelihood_threshold, double shrink_factor);
+int unb_popslice_iterate(unb_ctx *ctx, const double *slice_position, int64_t *n_running,
+                         int64_t *discarded);
+int unb_popslice_end(unb_ctx *ctx, double *allu, double *allp, double *allL, double *tleft,
+                     double *tright, int64_t *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,19 @@ SIGNATURES = {
     "unb_region_inside_loglike": [_c_vp, _sz, _c_vp, _c_vp, _int, _c_vp],
     "unb_region_inside_loglike_dev": [_c_vp, _sz, _c_vp, _c_vp, _int, _c_vp, _c_vp],
     "unb_region_refill": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp, _c_vp],
+    # population step-sampler helpers (ultranest/stepfuncs.pyx)
+    "unb_within_unit_cube": [_c_vp, _sz, _sz, _c_vp],
+    "unb_evolve_prepare": [_c_vp, _c_vp, _sz, _c_vp, _c_vp],
+    "unb_evolve_update": [_c_vp, _c_vp, _sz, _dbl, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                          _c_vp, _sz],
+    "unb_evolve": [_c_vp, _dbl, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _sz, _sz, _c_vp,
+                   _c_vp, _c_vp],
+    "unb_step_back": [_dbl, _c_vp, _sz, _sz, _c_vp, _c_vp],
+    "unb_update_vectorised_slice_sampler": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                                            _dbl, _dbl, _c_vp, _c_vp, _c_vp, _sz, _sz, _sz, _c_vp],
+    "unb_popslice_begin": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _sz, _sz, _dbl, _dbl],
+    "unb_popslice_iterate": [_c_vp, _c_vp, _c_vp],
+    "unb_popslice_end": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
 }
 # symbols without the leading ctx argument
 FREE_SIGNATURES = {
@@ -484,6 +497,34 @@ class Engine(object):
                   _ptr(like), _ptr(counts))
         del keep
         return flags, like, (int(counts[0]), int(counts[1]), int(counts[2]))
+
+
+class StepDesc(ctypes.Structure):
+    """``unb_step_desc`` of include/ultranest_b200.h."""
+    _fields_ = [("xform_kind", ctypes.c_int32), ("loglike_kind", ctypes.c_int32),
+                ("xform_scale", ctypes.c_void_p), ("xform_lo", ctypes.c_void_p),
+                ("lparams", ctypes.c_void_p)]
+
+
+def make_step_desc(ndim, xform, like_kind, lparams):
+    """``(desc, keepalive)`` for the fused step kernels; ``xform``: ``None`` or ``(scale, lo)``."""
+    keep = []
+    desc = StepDesc()
+    desc.loglike_kind = int(like_kind)
+    if xform is None:
+        desc.xform_kind = XFORM_IDENTITY
+    else:
+        sc = as_f64(np.broadcast_to(np.asarray(xform[0], dtype=float), (ndim,)))
+        lo = as_f64(np.broadcast_to(np.asarray(xform[1], dtype=float), (ndim,)))
+        keep += [sc, lo]
+        desc.xform_kind = XFORM_SCALE_SHIFT
+        desc.xform_scale = _ptr(sc)
+        desc.xform_lo = _ptr(lo)
+    if lparams is not None:
+        lp = as_f64(lparams)
+        keep.append(lp)
+        desc.lparams = _ptr(lp)
+    return desc, keep
 
 
 class RefillDesc(ctypes.Structure):

@@ -308,6 +308,8 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
     free_dev(ctx->boot_idx); free_dev(ctx->boot_meta); free_dev(ctx->boot_out);
     free_dev(ctx->boot_ell);
     free_pin(ctx->pin_small);
+    for (DevBuf &b : ctx->sf) free_dev(b);
+    free_dev(ctx->sf_params);
     delete ctx;
     return UNB_OK;
 }

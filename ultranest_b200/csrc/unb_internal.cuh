@@ -178,6 +178,14 @@ struct unb_ctx {
     // bootstrap scratch
     DevBuf boot_rows, boot_u, boot_tiles, boot_idx, boot_meta, boot_out, boot_ell;
     PinBuf pin_small;
+    // population step-sampler helpers (unb_stepfuncs.cu): scratch buffers + slice-loop session
+    DevBuf sf[14];
+    DevBuf sf_params;
+    bool ps_active = false;
+    size_t ps_popsize = 0, ps_ndim = 0, ps_count = 0;
+    int ps_xform_kind = 0, ps_loglike_kind = 0;
+    const double *ps_scale = nullptr, *ps_lo = nullptr, *ps_lparams = nullptr;
+    double ps_thr = 0.0, ps_shrink = 1.0;
 };
 
 // ---------------------------------------------------------------------------------------
