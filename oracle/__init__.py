@@ -4,11 +4,13 @@ Nothing in the product package (``ultranest_b200``) imports this.  Allowed users
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs.
 
-Two checkers live here:
+Three checkers live here:
 
 * :mod:`oracle.cport` -- ctypes wrappers around ``liboracle.so`` (``mlfriends_oracle.c``),
   a plain-C restatement of the reference's loops (each function cites
   ``ultranest/mlfriends.pyx`` lines).
+* :mod:`oracle.stepport` -- the same for ``libstepfuncs_oracle.so`` (``stepfuncs_oracle.c``), the
+  population step-sampler helpers of ``ultranest/stepfuncs.pyx``.
 * :func:`oracle.reference` -- the UNMODIFIED reference package, compiled by
   ``build_ref.py`` into the git-ignored ``oracle/_ref`` (travels to the GPU box).
 """
