@@ -176,6 +176,14 @@ ScanArgs scan_args_for(const LiveTiles &L)
     return a;
 }
 
+// largest squared norm of the live block for the certain-neighbour level of the fp32 membership
+// filter (unb_scan.cu, tile_filter32); UNB_ANY32_NOSURE=1 switches the shortcut off (A/B, tests)
+double sure_namax(const LiveTiles &L)
+{
+    static const bool off = getenv("UNB_ANY32_NOSURE") != nullptr;
+    return off ? (double)INFINITY : L.namax_host;
+}
+
 // threshold-mode h row + (when safe and enabled) the fp32 image used by the membership kernel
 int prepare_threshold(unb_ctx *ctx, LiveTiles &L, double r2, cudaStream_t s, ScanArgs *a)
 {
@@ -186,6 +194,7 @@ int prepare_threshold(unb_ctx *ctx, LiveTiles &L, double r2, cudaStream_t s, Sca
     if (a && ok32) {
         a->tiles32 = (const float *)L.tiles32.p;
         a->kappa32 = unb_kappa32(L.d);
+        a->namax32 = sure_namax(L);
     }
     return UNB_OK;
 }
@@ -865,6 +874,7 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
         if (have32) {
             a.tiles32 = (const float *)R.live.tiles32.p;   // prepared by the caller (set_h stage)
             a.kappa32 = unb_kappa32(R.live.d);
+            a.namax32 = sure_namax(R.live);
         }
         UNB_TRY(unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s));
     } else {
@@ -1235,6 +1245,7 @@ int has_neighbour_host(unb_ctx *ctx, LiveTiles &L, const double *tpts, size_t m,
     ScanArgs a = scan_args_for(L);
     a.tiles32 = pre.tiles32;
     a.kappa32 = pre.kappa32;
+    a.namax32 = pre.namax32;
     a.cand = (const double *)ln.cand.p;
     a.n_items = (long long)m;
     a.r2 = r2;
@@ -1289,6 +1300,7 @@ extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, 
     if (!nnearby_dev) {
         a.tiles32 = pre.tiles32;
         a.kappa32 = pre.kappa32;
+        a.namax32 = pre.namax32;
     }
     a.cand = tpts_dev;
     a.n_items = (long long)m;

@@ -674,9 +674,22 @@ constexpr int any32_min_blocks(int DR, int TM)
     return need <= 80 ? 5 : (need <= 128 ? 4 : (need <= 168 ? 3 : 2));
 }
 
+// Per slot and group of 4 live points only the MAXIMUM of the four accumulators is compared in
+// the common path (2-3 FMNMX + one FSETP instead of four compare/select/merge chains):
+//   max <  thr_lo            nothing flagged (the usual case);
+//   max >= thr_hi            a CERTAIN neighbour: with M = kappa32 (|a|^2_max + |b|^2 + r2) the
+//                            error budget of the filter (widening of h and thr, conversions,
+//                            chain: < kappa32 Q in total) gives  acc - thr >= M  =>  r2 - D > 0
+//                            by more than the fp64 rounding of the reference's own distance, so
+//                            the reference finds D <= r2 too and the slot retires without an
+//                            exact evaluation (membership only needs existence);
+//   otherwise                the flagged pairs of the group are recorded and decided exactly.
+// thr_lo = -inf (candidate out of the fp32 range) flags everything, thr_hi = +inf then.
 template <int DR, int TM, int TMA>
-__device__ __forceinline__ void tile_filter32(const float (&a)[TM][DR], const int (&thrkey)[TM],
-                                              unsigned long long (&pend)[TM], const float *T)
+__device__ __forceinline__ void tile_filter32(const float (&a)[TM][DR], float (&thr_lo)[TM],
+                                              const float (&thr_hi)[TM], const int (&row)[TM],
+                                              int (&hit)[TM], unsigned long long (&pend)[TM],
+                                              const float *T)
 {
 #pragma unroll 1
     for (int g = 0; g < REG_TILE_N / TN; g++) {
@@ -702,11 +715,21 @@ __device__ __forceinline__ void tile_filter32(const float (&a)[TM][DR], const in
         }
 #pragma unroll
         for (int m = 0; m < TMA; m++) {
-            unsigned nib = 0;
+            const float mx = fmaxf(fmaxf(acc[m][0], acc[m][1]), fmaxf(acc[m][2], acc[m][3]));
+            if (!(mx < thr_lo[m])) {            // also taken for NaN
+                if (row[m] >= 0 && !hit[m]) {
+                    if (mx >= thr_hi[m]) {
+                        hit[m] = 1;
+                        pend[m] = 0ull;
+                        thr_lo[m] = __int_as_float(0x7f800000);
+                    } else {
+                        unsigned nib = 0;
 #pragma unroll
-            for (int n = 0; n < TN; n++)
-                nib |= (__float_as_int(acc[m][n]) >= thrkey[m]) ? (1u << n) : 0u;
-            pend[m] |= (unsigned long long)nib << (g * TN);
+                        for (int n = 0; n < TN; n++) nib |= !(acc[m][n] < thr_lo[m]) ? (1u << n) : 0u;
+                        pend[m] |= (unsigned long long)nib << (g * TN);
+                    }
+                }
+            }
         }
     }
 }
@@ -721,7 +744,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
     constexpr int TILE_FLOATS = (DR + 1) * REG_TILE_N;
     constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
     float *tbuf = reinterpret_cast<float *>(smem_raw + 128);
-    uint32_t *stage = reinterpret_cast<uint32_t *>(tbuf + 2 * TILE_FLOATS);   // [DR+4][slots]
+    uint32_t *stage = reinterpret_cast<uint32_t *>(tbuf + 2 * TILE_FLOATS);   // [DR+5][slots]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -731,13 +754,17 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
     const int n_items = A.n_items_dev ? *A.n_items_dev : (int)A.n_items;
     const int d = A.d;
     const double thr_scale = __dmul_rn(0.5, __dsub_rn(1.0, A.kappa32));
+    // M = 1.001 kappa32 (|a|^2_max + r2 + |b|^2); namax32 = +inf switches the shortcut off
+    const double sure_scale = __dmul_rn(1.001, A.kappa32), sure_base = __dadd_rn(A.namax32, A.r2);
 
     float a[TM][DR];
-    int row[TM], orow[TM], rem[TM], thrkey[TM], hit[TM];
+    int row[TM], orow[TM], rem[TM], hit[TM];
+    float thr_lo[TM], thr_hi[TM];
     unsigned long long pend[TM];
 #pragma unroll
     for (int m = 0; m < TM; m++) {
-        row[m] = -1; orow[m] = -1; rem[m] = 0; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull;
+        row[m] = -1; orow[m] = -1; rem[m] = 0; hit[m] = 0; pend[m] = 0ull;
+        thr_lo[m] = __int_as_float(0x7f800000); thr_hi[m] = __int_as_float(0x7f800000);
 #pragma unroll
         for (int k = 0; k < DR; k++) a[m][k] = 0.f;
     }
@@ -750,7 +777,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                 A.out_mask[orow[m]] = hit[m] ? 1 : 0;
                 if (A.out_like && !hit[m]) A.out_like[orow[m]] = -pos_inf();
                 row[m] = -1;
-                thrkey[m] = INT_MAX;
+                thr_lo[m] = __int_as_float(0x7f800000);
             }
             const bool need = (row[m] < 0) && !exhausted;
             const unsigned ball = __ballot_sync(FULL, need);
@@ -771,9 +798,14 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                             a[m][k] = __double2float_rn(v);
                             nb = fma(v, v, nb);
                         }
-                        // threshold rounded DOWN; a zero / out-of-range norm flags everything
+                        // threshold rounded DOWN; a zero / out-of-range norm flags everything.
+                        // thr_hi = thr + M rounded UP: the certain-neighbour level (tile_filter32)
                         const float thr = __double2float_rd(__dmul_rn(nb, thr_scale));
-                        thrkey[m] = (nb < 1e30 && thr > 0.f) ? __float_as_int(thr) : INT_MIN;
+                        const bool in_range = nb < 1e30 && thr > 0.f;
+                        thr_lo[m] = in_range ? thr : -__int_as_float(0x7f800000);
+                        thr_hi[m] = in_range ? __double2float_ru(__dadd_rn(
+                                                   (double)thr, __dmul_rn(sure_scale, __dadd_rn(sure_base, nb))))
+                                             : __int_as_float(0x7f800000);
                         rem[m] = ntiles;
                         hit[m] = 0;
                     } else {
@@ -823,10 +855,10 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
         if (!warp_idle) {
             if (single) {
                 tile_units += 1;
-                tile_filter32<DR, TM, 1>(a, thrkey, pend, T);
+                tile_filter32<DR, TM, 1>(a, thr_lo, thr_hi, row, hit, pend, T);
             } else {
                 tile_units += TM;
-                tile_filter32<DR, TM, TM>(a, thrkey, pend, T);
+                tile_filter32<DR, TM, TM>(a, thr_lo, thr_hi, row, hit, pend, T);
             }
             // ---- decide in exact fp64 from the fp64 rows (global memory, L2 resident)
             const int tile_first = (int)((start + tt) % (unsigned)ntiles) * REG_TILE_N;
@@ -856,7 +888,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                         }
                         if (D <= A.r2) {
                             hit[m] = 1;
-                            thrkey[m] = INT_MAX;
+                            thr_lo[m] = __int_as_float(0x7f800000);
                             pend[m] = 0ull;
                         }
                     }
@@ -908,10 +940,11 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                     stage[(DR + 0) * ANY_STAGE_SLOTS + j] = (uint32_t)row[m];
                     stage[(DR + 1) * ANY_STAGE_SLOTS + j] = (uint32_t)orow[m];
                     stage[(DR + 2) * ANY_STAGE_SLOTS + j] = (uint32_t)rem[m];
-                    stage[(DR + 3) * ANY_STAGE_SLOTS + j] = (uint32_t)thrkey[m];
+                    stage[(DR + 3) * ANY_STAGE_SLOTS + j] = (uint32_t)__float_as_int(thr_lo[m]);
+                    stage[(DR + 4) * ANY_STAGE_SLOTS + j] = (uint32_t)__float_as_int(thr_hi[m]);
                     j++;
                 }
-                row[m] = -1; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull;
+                row[m] = -1; thr_lo[m] = __int_as_float(0x7f800000); hit[m] = 0; pend[m] = 0ull;
             }
             __syncthreads();
             if (tid < total) {
@@ -921,7 +954,8 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                 row[0] = (int)stage[(DR + 0) * ANY_STAGE_SLOTS + tid];
                 orow[0] = (int)stage[(DR + 1) * ANY_STAGE_SLOTS + tid];
                 rem[0] = (int)stage[(DR + 2) * ANY_STAGE_SLOTS + tid];
-                thrkey[0] = (int)stage[(DR + 3) * ANY_STAGE_SLOTS + tid];
+                thr_lo[0] = __int_as_float((int)stage[(DR + 3) * ANY_STAGE_SLOTS + tid]);
+                thr_hi[0] = __int_as_float((int)stage[(DR + 4) * ANY_STAGE_SLOTS + tid]);
             }
             __syncthreads();
             single = true;
@@ -967,13 +1001,17 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
     const int n_items = A.n_items_dev ? *A.n_items_dev : (int)A.n_items;
     const int d = A.d;
     const double thr_scale = __dmul_rn(0.5, __dsub_rn(1.0, A.kappa32));
+    // M = 1.001 kappa32 (|a|^2_max + r2 + |b|^2); namax32 = +inf switches the shortcut off
+    const double sure_scale = __dmul_rn(1.001, A.kappa32), sure_base = __dadd_rn(A.namax32, A.r2);
 
     float a[TM][DR];
-    int row[TM], orow[TM], rem[TM], thrkey[TM], hit[TM];
+    int row[TM], orow[TM], rem[TM], hit[TM];
+    float thr_lo[TM], thr_hi[TM];
     unsigned long long pend[TM];
 #pragma unroll
     for (int m = 0; m < TM; m++) {
-        row[m] = -1; orow[m] = -1; rem[m] = 0; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull;
+        row[m] = -1; orow[m] = -1; rem[m] = 0; hit[m] = 0; pend[m] = 0ull;
+        thr_lo[m] = __int_as_float(0x7f800000); thr_hi[m] = __int_as_float(0x7f800000);
 #pragma unroll
         for (int k = 0; k < DR; k++) a[m][k] = 0.f;
     }
@@ -986,7 +1024,7 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
                 A.out_mask[orow[m]] = hit[m] ? 1 : 0;
                 if (A.out_like && !hit[m]) A.out_like[orow[m]] = -pos_inf();
                 row[m] = -1;
-                thrkey[m] = INT_MAX;
+                thr_lo[m] = __int_as_float(0x7f800000);
             }
             const bool need = (row[m] < 0) && !exhausted;
             const unsigned ball = __ballot_sync(FULL, need);
@@ -1007,8 +1045,14 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
                             a[m][k] = __double2float_rn(v);
                             nb = fma(v, v, nb);
                         }
+                        // threshold rounded DOWN; a zero / out-of-range norm flags everything.
+                        // thr_hi = thr + M rounded UP: the certain-neighbour level (tile_filter32)
                         const float thr = __double2float_rd(__dmul_rn(nb, thr_scale));
-                        thrkey[m] = (nb < 1e30 && thr > 0.f) ? __float_as_int(thr) : INT_MIN;
+                        const bool in_range = nb < 1e30 && thr > 0.f;
+                        thr_lo[m] = in_range ? thr : -__int_as_float(0x7f800000);
+                        thr_hi[m] = in_range ? __double2float_ru(__dadd_rn(
+                                                   (double)thr, __dmul_rn(sure_scale, __dadd_rn(sure_base, nb))))
+                                             : __int_as_float(0x7f800000);
                         rem[m] = ntiles;
                         hit[m] = 0;
                     } else {
@@ -1053,10 +1097,10 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
         const float *T = tbuf + buf * TILE_FLOATS;
         if (single) {
             tile_units += 1;
-            tile_filter32<DR, TM, 1>(a, thrkey, pend, T);
+            tile_filter32<DR, TM, 1>(a, thr_lo, thr_hi, row, hit, pend, T);
         } else {
             tile_units += TM;
-            tile_filter32<DR, TM, TM>(a, thrkey, pend, T);
+            tile_filter32<DR, TM, TM>(a, thr_lo, thr_hi, row, hit, pend, T);
         }
         const int tile_first = (int)((start + tt) % (unsigned)ntiles) * REG_TILE_N;
 #pragma unroll
@@ -1083,7 +1127,7 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
                     }
                     if (D <= A.r2) {
                         hit[m] = 1;
-                        thrkey[m] = INT_MAX;
+                        thr_lo[m] = __int_as_float(0x7f800000);
                         pend[m] = 0ull;
                     }
                 }
@@ -1120,10 +1164,11 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
                     const int r_ = __shfl_sync(FULL, row[m], src);
                     const int o_ = __shfl_sync(FULL, orow[m], src);
                     const int e_ = __shfl_sync(FULL, rem[m], src);
-                    const int t_ = __shfl_sync(FULL, thrkey[m], src);
+                    const float t_ = __shfl_sync(FULL, thr_lo[m], src);
+                    const float th_ = __shfl_sync(FULL, thr_hi[m], src);
                     // which live lanes were adopted: the first popc(livem) free lanes took them all
-                    if (takes) { row[0] = r_; orow[0] = o_; rem[0] = e_; thrkey[0] = t_; hit[0] = 0; pend[0] = 0ull; }
-                    if ((livem >> lane) & 1u) { row[m] = -1; thrkey[m] = INT_MAX; hit[m] = 0; pend[m] = 0ull; }
+                    if (takes) { row[0] = r_; orow[0] = o_; rem[0] = e_; thr_lo[0] = t_; thr_hi[0] = th_; hit[0] = 0; pend[0] = 0ull; }
+                    if ((livem >> lane) & 1u) { row[m] = -1; thr_lo[m] = __int_as_float(0x7f800000); hit[m] = 0; pend[m] = 0ull; }
                 }
             }
             bool upper = false;
@@ -1521,7 +1566,7 @@ int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t 
         UNB_CUDA(ctx, cudaGetLastError());
         return UNB_OK;
     }
-    const size_t smem = 128 + (2 * (size_t)(DR + 1) * REG_TILE_N + (size_t)(DR + 4) * ANY_STAGE_SLOTS) *
+    const size_t smem = 128 + (2 * (size_t)(DR + 1) * REG_TILE_N + (size_t)(DR + 5) * ANY_STAGE_SLOTS) *
                                   sizeof(float);
     static int per_sm = 0;   // per instantiation; the engine drives one device per process
     if (per_sm == 0) {
