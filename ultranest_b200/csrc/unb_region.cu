@@ -121,19 +121,78 @@ __global__ void k_prep(const PrepArgs P)
 // proposals are read from HBM exactly once.
 // ---------------------------------------------------------------------------------------
 
-#ifndef UNB_PREP_MINB
-#define UNB_PREP_MINB 1
-#endif
+// resident blocks the register kernel is compiled for (register cap 128 / 168 / 255)
+constexpr int prep_min_blocks(int DR) { return DR <= 20 ? 5 : (DR <= 24 ? 4 : (DR <= 28 ? 3 : 2)); }
+
+// NumPy's pairwise sum (pw_block, n <= 128) of a register vector: every index is a compile-time
+// constant after unrolling, so the terms never leave the register file.
+template <int DR>
+__device__ __forceinline__ double pw_sum_regs(const double (&t)[DR], int n)
+{
+    if (DR < 8 || n < 8) {
+        double res = 0.0;
+#pragma unroll
+        for (int i = 0; i < DR; i++)
+            if (i < n) res = __dadd_rn(res, t[i]);
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) r[q] = t[q < DR ? q : 0];
+    const int n8 = n - (n % 8);
+#pragma unroll
+    for (int i = 8; i + 8 <= DR; i += 8) {
+        if (i < n8) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) r[q] = __dadd_rn(r[q], t[i + q]);
+        }
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+    for (int i = 8; i < DR; i++)
+        if (i >= n8 && i < n) res = __dadd_rn(res, t[i]);
+    return res;
+}
+
+// the built-in likelihoods of loglike_row for a row held in registers (same arithmetic)
+template <int DR>
+__device__ __forceinline__ double loglike_regs(int kind, const double (&p)[DR], const double *row, int d,
+                                               const double *lp)
+{
+    double t[DR];
+    if (kind == UNB_LOGLIKE_GAUSS) {
+        const double sigma = __ldg(lp + d), norm_const = __ldg(lp + d + 1);
+#pragma unroll
+        for (int i = 0; i < DR; i++) {
+            const double z = (i < d) ? __ddiv_rn(__dsub_rn(p[i], __ldg(lp + i)), sigma) : 0.0;
+            t[i] = __dmul_rn(z, z);
+        }
+        return __dsub_rn(__dmul_rn(-0.5, pw_sum_regs<DR>(t, d)), norm_const);
+    } else if (kind == UNB_LOGLIKE_ROSENBROCK) {
+#pragma unroll
+        for (int i = 0; i < DR; i++) {
+            const double a = p[i], b = p[i + 1 < DR ? i + 1 : i];
+            const double u = __dsub_rn(b, __dmul_rn(a, a));
+            const double v = __dsub_rn(1.0, a);
+            t[i] = __dadd_rn(__dmul_rn(100.0, __dmul_rn(u, u)), __dmul_rn(v, v));
+        }
+        return __dmul_rn(-2.0, pw_sum_regs<DR>(t, d - 1));
+    }
+    // eggbox: cos() is a long routine -- a rolled loop over the row in memory (L1 resident)
+    // instead of DR inlined copies
+    double chi = 1.0;
+#pragma unroll 1
+    for (int i = 0; i < d; i++) chi = __dmul_rn(chi, cos(__ddiv_rn(row[i], 2.0)));
+    return pow(__dadd_rn(2.0, chi), 5.0);
+}
 
 template <int DR>
-__global__ void __launch_bounds__(128, UNB_PREP_MINB) k_prep_reg(const PrepArgs P)
+__device__ __forceinline__ void prep_load_row(const PrepArgs &P, long long j, bool vec, double (&p)[DR])
 {
-    extern __shared__ __align__(16) double rowbuf[];
     const int d = P.d;
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = j < P.m;
-    double p[DR];
-    if ((d & 1) == 0 && (reinterpret_cast<uintptr_t>(P.pts) & 15) == 0) {
+    if (vec) {
         // even d: rows are 16-byte aligned, read them as 128-bit loads
         const double2 *row2 = reinterpret_cast<const double2 *>(P.pts + j * d);
 #pragma unroll
@@ -147,79 +206,99 @@ __global__ void __launch_bounds__(128, UNB_PREP_MINB) k_prep_reg(const PrepArgs 
 #pragma unroll
         for (int k = 0; k < DR; k++) p[k] = (valid && k < d) ? P.pts[j * d + k] : 0.0;
     }
-    bool inside = valid;
-    if (P.center) {
-        double dl[DR];
+}
+
+template <int DR>
+__global__ void __launch_bounds__(128, prep_min_blocks(DR)) k_prep_reg(const PrepArgs P)
+{
+    const int d = P.d;
+    const bool vec = (d & 1) == 0 && (reinterpret_cast<uintptr_t>(P.pts) & 15) == 0;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double p[DR];
+    prep_load_row<DR>(P, j, vec, p);
+    {
+        const bool valid = j < P.m;
+        bool inside = valid;
+        if (P.center) {
+            double dl[DR];
 #pragma unroll
-        for (int k = 0; k < DR; k++) dl[k] = __dsub_rn(p[k], c_ell_center[k]);
-        // filter: r_fast = d^T (A d) with fused multiply-adds (d^2 + 2d DFMA instead of the
-        // einsum's 3 d^2 non-fused operations).  Both r_fast and the reference's sequential
-        // einsum value lie within (d^2+2d+4) u * sum|d_j A_jk d_k| <= tol of d^T A d, with
-        // sum|...| <= |d|^2 ||A||_F, so outside the band [r2 - tol, r2 + tol] the comparison
-        // is already decided; inside the band the exact einsum order decides.
-        double nd = 0.0, rfast = 0.0;
+            for (int k = 0; k < DR; k++) dl[k] = __dsub_rn(p[k], c_ell_center[k]);
+            // filter: r_fast = d^T (A d) with fused multiply-adds (d^2 + 2d DFMA instead of the
+            // einsum's 3 d^2 non-fused operations).  Both r_fast and the reference's sequential
+            // einsum value lie within (d^2+2d+4) u * sum|d_j A_jk d_k| <= tol of d^T A d, with
+            // sum|...| <= |d|^2 ||A||_F, so outside the band [r2 - tol, r2 + tol] the comparison
+            // is already decided; inside the band the exact einsum order decides.
+            double nd = 0.0, rfast = 0.0;
 #pragma unroll
-        for (int jj = 0; jj < DR; jj++) {
-            double y = 0.0;
+            for (int jj = 0; jj < DR; jj++) {
+                double y = 0.0;
 #pragma unroll
-            for (int k = 0; k < DR; k++) y = fma(c_ell_invcov[jj * DR + k], dl[k], y);
-            rfast = fma(dl[jj], y, rfast);
-            nd = fma(dl[jj], dl[jj], nd);
+                for (int k = 0; k < DR; k++) y = fma(c_ell_invcov[jj * DR + k], dl[k], y);
+                rfast = fma(dl[jj], y, rfast);
+                nd = fma(dl[jj], dl[jj], nd);
+            }
+            const double tol = __dmul_rn(P.ell_tol_scale, nd);
+            bool in = rfast <= P.r2;
+            const bool band = !(fabs(__dsub_rn(rfast, P.r2)) > tol);   // also true for NaN
+            if (__any_sync(FULL, band && valid)) {
+                if (band) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < DR; jj++)
+#pragma unroll
+                        for (int k = 0; k < DR; k++)
+                            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dl[jj], c_ell_invcov[jj * DR + k]), dl[k]));
+                    in = acc <= P.r2;
+                }
+            }
+            inside = valid && in;
+            if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
         }
-        const double tol = __dmul_rn(P.ell_tol_scale, nd);
-        bool in = rfast <= P.r2;
-        const bool band = !(fabs(__dsub_rn(rfast, P.r2)) > tol);   // also true for NaN
-        if (__any_sync(FULL, band && valid)) {
-            if (band) {
-                double acc = 0.0;
+        if (P.like && valid) {
+            double like = -__longlong_as_double(0x7ff0000000000000LL);
+            if (inside) like = loglike_regs<DR>(P.loglike_kind, p, P.pts + j * d, d, P.lparams);
+            P.like[j] = like;
+        }
+        if (P.layer_kind >= 0) {
+            const unsigned ball = __ballot_sync(FULL, inside);
+            int base = 0;
+            if ((threadIdx.x & 31) == 0 && ball) base = atomicAdd(P.n_items, __popc(ball));
+            base = __shfl_sync(FULL, base, 0);
+            if (inside) {
+                const int pos = base + __popc(ball & ((1u << (threadIdx.x & 31)) - 1));
+                P.items[pos] = (int)j;
+                double *out = P.tcand + (size_t)pos * d;
+                double o[DR];
+                if (P.layer_kind == UNB_LAYER_AFFINE) {
+                    double x[DR];
 #pragma unroll
-                for (int jj = 0; jj < DR; jj++)
+                    for (int k = 0; k < DR; k++) x[k] = __dsub_rn(p[k], c_xf_shift[k]);
+#pragma unroll
+                    for (int jj = 0; jj < DR; jj++) {
+                        double t = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DR; k++) t = fma(x[k], c_xf_mat[k * DR + jj], t);
+                        o[jj] = t;
+                    }
+                } else if (P.layer_kind == UNB_LAYER_SCALING) {
+#pragma unroll
+                    for (int k = 0; k < DR; k++) o[k] = __ddiv_rn(__dsub_rn(p[k], c_xf_shift[k]), c_xf_mat[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < DR; k++) o[k] = p[k];
+                }
+                if ((d & 1) == 0 && (reinterpret_cast<uintptr_t>(P.tcand) & 15) == 0) {
+                    double2 *out2 = reinterpret_cast<double2 *>(out);   // pos * d is even
+#pragma unroll
+                    for (int k = 0; k < DR; k += 2)
+                        if (k < d) out2[k >> 1] = make_double2(o[k], o[k + 1]);
+                } else {
 #pragma unroll
                     for (int k = 0; k < DR; k++)
-                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dl[jj], c_ell_invcov[jj * DR + k]), dl[k]));
-                in = acc <= P.r2;
+                        if (k < d) out[k] = o[k];
+                }
             }
         }
-        inside = valid && in;
-        if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
-    }
-    if (P.like && valid) {
-        double like = -__longlong_as_double(0x7ff0000000000000LL);
-        if (inside) {
-            double *t = rowbuf + (size_t)threadIdx.x * odd_stride(d);
-            like = loglike_row(P.loglike_kind, P.pts + j * d, d, t, P.lparams);
-        }
-        P.like[j] = like;
-    }
-    if (P.layer_kind < 0) return;
-
-    const unsigned ball = __ballot_sync(FULL, inside);
-    int base = 0;
-    if ((threadIdx.x & 31) == 0 && ball) base = atomicAdd(P.n_items, __popc(ball));
-    base = __shfl_sync(FULL, base, 0);
-    if (!inside) return;
-    const int pos = base + __popc(ball & ((1u << (threadIdx.x & 31)) - 1));
-    P.items[pos] = (int)j;
-    double *out = P.tcand + (size_t)pos * d;
-    if (P.layer_kind == UNB_LAYER_AFFINE) {
-        double x[DR];
-#pragma unroll
-        for (int k = 0; k < DR; k++) x[k] = __dsub_rn(p[k], c_xf_shift[k]);
-#pragma unroll
-        for (int jj = 0; jj < DR; jj++) {
-            double t = 0.0;
-#pragma unroll
-            for (int k = 0; k < DR; k++) t = fma(x[k], c_xf_mat[k * DR + jj], t);
-            if (jj < d) out[jj] = t;
-        }
-    } else if (P.layer_kind == UNB_LAYER_SCALING) {
-#pragma unroll
-        for (int k = 0; k < DR; k++)
-            if (k < d) out[k] = __ddiv_rn(__dsub_rn(p[k], c_xf_shift[k]), c_xf_mat[k]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < DR; k++)
-            if (k < d) out[k] = p[k];
     }
 }
 
@@ -744,8 +823,7 @@ int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s)
 template <int DR>
 static int launch_prep_reg(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s)
 {
-    const size_t smem = p.like ? (size_t)128 * odd_stride(p.d) * sizeof(double) : 0;
-    k_prep_reg<DR><<<(unsigned)((p.m + 127) / 128), 128, smem, s>>>(p);
+    k_prep_reg<DR><<<(unsigned)((p.m + 127) / 128), 128, 0, s>>>(p);
     ctx->launches++;
     UNB_CUDA(ctx, cudaGetLastError());
     return UNB_OK;
