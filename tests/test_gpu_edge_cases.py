@@ -98,6 +98,38 @@ def test_tiny_live_sets(eng, n, d):
     assert (eng.region_find_nearby(b) == want).all()
 
 
+@pytest.mark.parametrize("n,d,m", [(70, 20, 3), (70, 20, 40000), (4000, 20, 300000), (130, 5, 70000), (100, 50, 20000)])
+def test_membership_odd_candidates_and_drain(eng, n, d, m):
+    """Proposals the fp32 pre-filter cannot bound (zero norm, norm beyond the fp32 range: they flag
+    every pair, padded tile slots included) and launches whose tail runs through the cooperative
+    drain: the mask is still the oracle's."""
+    rng = np.random.RandomState(n + d + m)
+    a = 0.3 + 0.2 * _ball(rng, n, d)            # the origin is far outside every ball
+    b = 0.3 + 0.25 * _ball(rng, m, d)
+    b[0] = 0.0                                   # |b|^2 = 0
+    b[1] = 1e16                                  # |b|^2 > 1e30
+    b[2] = a[n - 1]                              # a live point itself
+    if m > 10:
+        b[m // 2] = 0.0
+        b[m - 1] = -3e15
+    r2 = 0.02
+    eng.region_sync_live(a)
+    eng.region_set_radius(r2)
+    got = eng.region_has_neighbour(b)
+    sub = np.unique(np.concatenate([np.arange(min(m, 3000)), [m // 2, m - 1]]))
+    want = cport.find_nearby(a, b[sub], r2) >= 0
+    assert (got[sub] == want).all()
+    assert not got[0] and not got[1] and got[2]
+    # every proposal through the exact-only kernels as well
+    from ultranest_b200 import _native
+    eng.set_option(_native.OPT_EXACT_ONLY, 1)
+    try:
+        eng.region_sync_live(a)
+        assert (eng.region_has_neighbour(b) == got).all()
+    finally:
+        eng.set_option(_native.OPT_EXACT_ONLY, 0)
+
+
 def test_chunked_host_pipeline_boundaries(eng):
     """inside() through several chunk sizes (incl. a ragged last chunk, both lanes) and through
     pageable as well as pinned caller buffers."""

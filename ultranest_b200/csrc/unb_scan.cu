@@ -434,6 +434,7 @@ __device__ __forceinline__ void tile_filter(const double (&a)[TM][DR], const int
 }
 
 constexpr int ANY_STAGE_SLOTS = SCAN_THREADS;   // capacity of the compaction staging area
+constexpr int ANY_COOP_MAX = 48;                // survivors per block at which the drain turns cooperative
 
 template <int DR, int TM>
 __global__ void __launch_bounds__(SCAN_THREADS, reg_min_blocks(DR, TM))
@@ -869,6 +870,9 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                         const int col = __ffsll((long long)pend[m]) - 1;
                         pend[m] &= pend[m] - 1ull;
                         rechecks++;
+                        // padded slots of the last tile are only ever flagged by a proposal that
+                        // flags everything (out-of-range norm): they are no live points
+                        if (tile_first + col >= A.n_live) continue;
                         const double *lp = A.live_rows + (size_t)(tile_first + col) * d;
                         const double *cp = A.cand + (size_t)row[m] * d;
                         // loads are issued in batches of 2 x 12 so that one L2 round trip covers
@@ -928,6 +932,103 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
             tma_bulk_g2s(tbuf + buf * TILE_FLOATS,
                          tiles + (size_t)((start + tt + 2) % (unsigned)ntiles) * TILE_FLOATS,
                          TILE_BYTES, &bars[buf]);
+        }
+        if (all_exh && total <= ANY_COOP_MAX) {
+            // ---- cooperative drain.  The last few proposals of a block are the unlucky long
+            // scans; one proposal per lane would stream the remaining tiles at the price of a
+            // full warp each.  Instead the survivors move to shared memory and every warp takes
+            // one survivor at a time with its LANES spread over the tile's live points (lane l:
+            // points 2l, 2l+1), so a tile costs ~4 DR instructions per survivor instead of
+            // ~80 DR per warp, and the tail of the launch shrinks accordingly.
+            int j = warp_off + incl - mine;
+#pragma unroll
+            for (int m = 0; m < TM; m++) {
+                if (row[m] >= 0) {
+#pragma unroll
+                    for (int k = 0; k < DR; k++)
+                        stage[k * ANY_STAGE_SLOTS + j] = (uint32_t)__float_as_int(a[m][k]);
+                    stage[(DR + 0) * ANY_STAGE_SLOTS + j] = (uint32_t)row[m];
+                    stage[(DR + 1) * ANY_STAGE_SLOTS + j] = (uint32_t)orow[m];
+                    stage[(DR + 2) * ANY_STAGE_SLOTS + j] = (uint32_t)rem[m];
+                    stage[(DR + 3) * ANY_STAGE_SLOTS + j] = (uint32_t)__float_as_int(thr_lo[m]);
+                    stage[(DR + 4) * ANY_STAGE_SLOTS + j] = (uint32_t)__float_as_int(thr_hi[m]);
+                    j++;
+                }
+                row[m] = -1;
+            }
+            volatile int *alive = s_info + 15;
+            if (tid == 0) *alive = total;
+            __syncthreads();
+            unsigned int coop_units = 0;
+            for (unsigned t2 = tt + 1;; t2++) {
+                const int b2 = t2 & 1;
+                mbar_wait(&bars[b2], (t2 >> 1) & 1);
+                const float *T2 = tbuf + b2 * TILE_FLOATS;
+                const int first2 = (int)((start + t2) % (unsigned)ntiles) * REG_TILE_N;
+                for (int j2 = warp; j2 < total; j2 += SCAN_THREADS / 32) {
+                    const int r2_ = (int)stage[(DR + 0) * ANY_STAGE_SLOTS + j2];
+                    if (r2_ < 0) continue;   // finished earlier (warp-uniform)
+                    coop_units++;
+                    const float tl = __int_as_float((int)stage[(DR + 3) * ANY_STAGE_SLOTS + j2]);
+                    const float th = __int_as_float((int)stage[(DR + 4) * ANY_STAGE_SLOTS + j2]);
+                    const float2 h = *reinterpret_cast<const float2 *>(T2 + DR * REG_TILE_N + 2 * lane);
+                    float acc0 = h.x, acc1 = h.y;
+#pragma unroll
+                    for (int k = 0; k < DR; k++) {
+                        const float c = __int_as_float((int)stage[k * ANY_STAGE_SLOTS + j2]);
+                        const float2 bb = *reinterpret_cast<const float2 *>(T2 + k * REG_TILE_N + 2 * lane);
+                        acc0 = fmaf(c, bb.x, acc0);
+                        acc1 = fmaf(c, bb.y, acc1);
+                    }
+                    const bool f0 = !(acc0 < tl), f1 = !(acc1 < tl);   // also true for NaN
+                    bool found = __any_sync(FULL, (acc0 >= th) || (acc1 >= th));
+                    if (!found && __any_sync(FULL, f0 || f1)) {
+                        // uncertain shell: every lane decides its own flagged pairs exactly
+                        bool ok = false;
+                        const double *cp = A.cand + (size_t)r2_ * d;
+#pragma unroll 1
+                        for (int which = 0; which < 2; which++) {
+                            if ((which == 0 ? f0 : f1) && !ok && first2 + 2 * lane + which < A.n_live) {
+                                const double *lp = A.live_rows + (size_t)(first2 + 2 * lane + which) * d;
+                                double D = 0.0;
+                                for (int kk = 0; kk < d; kk++) D = sq_step(D, __ldg(lp + kk), __ldg(cp + kk));
+                                ok = D <= A.r2;
+                                rechecks++;
+                            }
+                        }
+                        found = __any_sync(FULL, ok);
+                    }
+                    const int rem2 = (int)stage[(DR + 2) * ANY_STAGE_SLOTS + j2] - 1;
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (found || rem2 <= 0) {
+                            const int o2 = (int)stage[(DR + 1) * ANY_STAGE_SLOTS + j2];
+                            A.out_mask[o2] = found ? 1 : 0;
+                            if (A.out_like && !found) A.out_like[o2] = -pos_inf();
+                            stage[(DR + 0) * ANY_STAGE_SLOTS + j2] = 0xffffffffu;
+                            atomicSub((int *)alive, 1);
+                        } else {
+                            stage[(DR + 2) * ANY_STAGE_SLOTS + j2] = (uint32_t)rem2;
+                        }
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
+                const int left = *alive;
+                __syncthreads();
+                if (left == 0) {
+                    mbar_wait(&bars[(t2 + 1) & 1], ((t2 + 1) >> 1) & 1);   // tile t2+1 is in flight
+                    break;
+                }
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&bars[b2], TILE_BYTES);
+                    tma_bulk_g2s(tbuf + b2 * TILE_FLOATS,
+                                 tiles + (size_t)((start + t2 + 2) % (unsigned)ntiles) * TILE_FLOATS,
+                                 TILE_BYTES, &bars[b2]);
+                }
+            }
+            tile_units += (coop_units + 31) / 32;   // one survivor-tile = 1/32 of a warp-tile of filter work
+            break;
         }
         if (all_exh && total <= cap / 2 && total <= ANY_STAGE_SLOTS) {
             int j = warp_off + incl - mine;
@@ -1110,6 +1211,7 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
                     const int col = __ffsll((long long)pend[m]) - 1;
                     pend[m] &= pend[m] - 1ull;
                     rechecks++;
+                    if (tile_first + col >= A.n_live) continue;   // padded slot, no live point
                     const double *lp = A.live_rows + (size_t)(tile_first + col) * d;
                     const double *cp = A.cand + (size_t)row[m] * d;
                     double D = 0.0;
