@@ -87,6 +87,7 @@ struct ScanArgs {
     const double *tiles;      // tiled live block (of this launch / of round 0); NULL -> exact kernel
     const float *tiles32;     // fp32 tiles (membership kernel with the fp32 pre-filter), nullable
     double kappa32;           // slack factor of the fp32 filter
+    int coop_max;             // block membership kernel: survivors at which the drain turns cooperative
     double namax32;           // max squared norm of the live block (certain-neighbour level); +inf: off
     const double *live_rows;  // row-major (n x d) live block (plain exact kernel)
     const int *live_idx;      // nullable: exact kernel scans rows live_idx[i] (bootstrap rounds)

@@ -434,7 +434,8 @@ __device__ __forceinline__ void tile_filter(const double (&a)[TM][DR], const int
 }
 
 constexpr int ANY_STAGE_SLOTS = SCAN_THREADS;   // capacity of the compaction staging area
-constexpr int ANY_COOP_MAX = 48;                // survivors per block at which the drain turns cooperative
+constexpr int COOP_G = 4;                       // survivors a warp advances together in the cooperative drain
+constexpr int ANY_COOP_MAX = 24;                // survivors per block at which the drain turns cooperative
 
 template <int DR, int TM>
 __global__ void __launch_bounds__(SCAN_THREADS, reg_min_blocks(DR, TM))
@@ -933,7 +934,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                          tiles + (size_t)((start + tt + 2) % (unsigned)ntiles) * TILE_FLOATS,
                          TILE_BYTES, &bars[buf]);
         }
-        if (all_exh && total <= ANY_COOP_MAX) {
+        if (all_exh && total <= A.coop_max) {
             // ---- cooperative drain.  The last few proposals of a block are the unlucky long
             // scans; one proposal per lane would stream the remaining tiles at the price of a
             // full warp each.  Instead the survivors move to shared memory and every warp takes
@@ -965,53 +966,72 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                 mbar_wait(&bars[b2], (t2 >> 1) & 1);
                 const float *T2 = tbuf + b2 * TILE_FLOATS;
                 const int first2 = (int)((start + t2) % (unsigned)ntiles) * REG_TILE_N;
-                for (int j2 = warp; j2 < total; j2 += SCAN_THREADS / 32) {
-                    const int r2_ = (int)stage[(DR + 0) * ANY_STAGE_SLOTS + j2];
-                    if (r2_ < 0) continue;   // finished earlier (warp-uniform)
-                    coop_units++;
-                    const float tl = __int_as_float((int)stage[(DR + 3) * ANY_STAGE_SLOTS + j2]);
-                    const float th = __int_as_float((int)stage[(DR + 4) * ANY_STAGE_SLOTS + j2]);
+                // COOP_G survivors per warp pass: independent FFMA chains hide each other's latency
+                for (int j0 = warp; j0 < total; j0 += (SCAN_THREADS / 32) * COOP_G) {
+                    int jg[COOP_G], rg[COOP_G];
+                    bool any_act = false;
+#pragma unroll
+                    for (int g = 0; g < COOP_G; g++) {
+                        const int jj = j0 + g * (SCAN_THREADS / 32);
+                        jg[g] = jj < total ? jj : total - 1;
+                        rg[g] = jj < total ? (int)stage[(DR + 0) * ANY_STAGE_SLOTS + jj] : -1;
+                        any_act |= rg[g] >= 0;   // finished earlier: warp-uniform
+                    }
+                    if (!any_act) continue;
                     const float2 h = *reinterpret_cast<const float2 *>(T2 + DR * REG_TILE_N + 2 * lane);
-                    float acc0 = h.x, acc1 = h.y;
+                    float acc0[COOP_G], acc1[COOP_G];
+#pragma unroll
+                    for (int g = 0; g < COOP_G; g++) { acc0[g] = h.x; acc1[g] = h.y; }
 #pragma unroll
                     for (int k = 0; k < DR; k++) {
-                        const float c = __int_as_float((int)stage[k * ANY_STAGE_SLOTS + j2]);
                         const float2 bb = *reinterpret_cast<const float2 *>(T2 + k * REG_TILE_N + 2 * lane);
-                        acc0 = fmaf(c, bb.x, acc0);
-                        acc1 = fmaf(c, bb.y, acc1);
+#pragma unroll
+                        for (int g = 0; g < COOP_G; g++) {
+                            const float c = __int_as_float((int)stage[k * ANY_STAGE_SLOTS + jg[g]]);
+                            acc0[g] = fmaf(c, bb.x, acc0[g]);
+                            acc1[g] = fmaf(c, bb.y, acc1[g]);
+                        }
                     }
-                    const bool f0 = !(acc0 < tl), f1 = !(acc1 < tl);   // also true for NaN
-                    bool found = __any_sync(FULL, (acc0 >= th) || (acc1 >= th));
-                    if (!found && __any_sync(FULL, f0 || f1)) {
-                        // uncertain shell: every lane decides its own flagged pairs exactly
-                        bool ok = false;
-                        const double *cp = A.cand + (size_t)r2_ * d;
+#pragma unroll
+                    for (int g = 0; g < COOP_G; g++) {
+                        if (rg[g] < 0) continue;
+                        const int j2 = jg[g], r2_ = rg[g];
+                        coop_units++;
+                        const float tl = __int_as_float((int)stage[(DR + 3) * ANY_STAGE_SLOTS + j2]);
+                        const float th = __int_as_float((int)stage[(DR + 4) * ANY_STAGE_SLOTS + j2]);
+                        const bool f0 = !(acc0[g] < tl), f1 = !(acc1[g] < tl);   // also true for NaN
+                        bool found = __any_sync(FULL, (acc0[g] >= th) || (acc1[g] >= th));
+                        if (!found && __any_sync(FULL, f0 || f1)) {
+                            // uncertain shell: every lane decides its own flagged pairs exactly
+                            bool ok = false;
+                            const double *cp = A.cand + (size_t)r2_ * d;
 #pragma unroll 1
-                        for (int which = 0; which < 2; which++) {
-                            if ((which == 0 ? f0 : f1) && !ok && first2 + 2 * lane + which < A.n_live) {
-                                const double *lp = A.live_rows + (size_t)(first2 + 2 * lane + which) * d;
-                                double D = 0.0;
-                                for (int kk = 0; kk < d; kk++) D = sq_step(D, __ldg(lp + kk), __ldg(cp + kk));
-                                ok = D <= A.r2;
-                                rechecks++;
+                            for (int which = 0; which < 2; which++) {
+                                if ((which == 0 ? f0 : f1) && !ok && first2 + 2 * lane + which < A.n_live) {
+                                    const double *lp = A.live_rows + (size_t)(first2 + 2 * lane + which) * d;
+                                    double D = 0.0;
+                                    for (int kk = 0; kk < d; kk++) D = sq_step(D, __ldg(lp + kk), __ldg(cp + kk));
+                                    ok = D <= A.r2;
+                                    rechecks++;
+                                }
+                            }
+                            found = __any_sync(FULL, ok);
+                        }
+                        const int rem2 = (int)stage[(DR + 2) * ANY_STAGE_SLOTS + j2] - 1;
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (found || rem2 <= 0) {
+                                const int o2 = (int)stage[(DR + 1) * ANY_STAGE_SLOTS + j2];
+                                A.out_mask[o2] = found ? 1 : 0;
+                                if (A.out_like && !found) A.out_like[o2] = -pos_inf();
+                                stage[(DR + 0) * ANY_STAGE_SLOTS + j2] = 0xffffffffu;
+                                atomicSub((int *)alive, 1);
+                            } else {
+                                stage[(DR + 2) * ANY_STAGE_SLOTS + j2] = (uint32_t)rem2;
                             }
                         }
-                        found = __any_sync(FULL, ok);
+                        __syncwarp();
                     }
-                    const int rem2 = (int)stage[(DR + 2) * ANY_STAGE_SLOTS + j2] - 1;
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (found || rem2 <= 0) {
-                            const int o2 = (int)stage[(DR + 1) * ANY_STAGE_SLOTS + j2];
-                            A.out_mask[o2] = found ? 1 : 0;
-                            if (A.out_like && !found) A.out_like[o2] = -pos_inf();
-                            stage[(DR + 0) * ANY_STAGE_SLOTS + j2] = 0xffffffffu;
-                            atomicSub((int *)alive, 1);
-                        } else {
-                            stage[(DR + 2) * ANY_STAGE_SLOTS + j2] = (uint32_t)rem2;
-                        }
-                    }
-                    __syncwarp();
                 }
                 __syncthreads();
                 const int left = *alive;
@@ -1680,7 +1700,14 @@ int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t 
     const long long resident = (long long)per_sm * ctx->sm_count;
     if (bx > resident) bx = resident;
     if (bx < 1) bx = 1;
-    k_inside_any32<DR, TM><<<(unsigned)bx, SCAN_THREADS, smem, s>>>(a, queue_head);
+    static const int coop_max = []() {
+        const char *e = getenv("UNB_ANY32_COOP");   // experiment switch
+        int v = e ? atoi(e) : ANY_COOP_MAX;
+        return v < 0 ? 0 : (v > ANY_STAGE_SLOTS ? ANY_STAGE_SLOTS : v);
+    }();
+    ScanArgs ac = a;
+    ac.coop_max = coop_max;
+    k_inside_any32<DR, TM><<<(unsigned)bx, SCAN_THREADS, smem, s>>>(ac, queue_head);
     ctx->launches++;
     UNB_CUDA(ctx, cudaGetLastError());
     return UNB_OK;
