@@ -40,9 +40,12 @@ int set_smem(unb_ctx *ctx, K kernel, size_t bytes)
 
 // region parameters in __constant__ memory, row stride dr = d rounded up to 4, zero padded
 constexpr int PREP_MAXD = 32;     // register kernel
-constexpr int CONST_MAXD = 56;    // parameters in __constant__ memory (2 x 56^2 doubles = 50 KB)
+constexpr int CONST_MAXD = 32;    // parameters in __constant__ memory (3 x 32^2 doubles = 24 KB)
 __constant__ double c_ell_center[CONST_MAXD];
 __constant__ double c_ell_invcov[CONST_MAXD * CONST_MAXD];
+// inverse covariance FOLDED onto the upper triangle (S_jj = A_jj, S_jk = A_jk + A_kj for j < k,
+// 0 below): d^T A d = sum_{j<=k} d_j S_jk d_k -- half the multiply-adds of the ellipsoid filter
+__constant__ double c_ell_fold[CONST_MAXD * CONST_MAXD];
 __constant__ double c_xf_shift[CONST_MAXD];
 __constant__ double c_xf_mat[CONST_MAXD * CONST_MAXD];
 
@@ -62,22 +65,13 @@ __global__ void k_prep(const PrepArgs P)
         if (valid) {
             const double *p = P.pts + j * d;
             for (int k = 0; k < d; k++)
-                my[k] = __dsub_rn(p[k], P.use_constants ? c_ell_center[k] : __ldg(P.center + k));
+                my[k] = __dsub_rn(p[k], __ldg(P.center + k));
             // np.einsum('ij,jk,ik->i'): acc += (d_j * A_jk) * d_k, j outer, k inner
-            if (P.use_constants) {   // 32 < d <= 56: matrix through the constant cache (uniform index)
-                const int dr = (d + 3) / 4 * 4;
-                for (int jj = 0; jj < d; jj++) {
-                    const double dj = my[jj];
-                    for (int k = 0; k < d; k++)
-                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, c_ell_invcov[jj * dr + k]), my[k]));
-                }
-            } else {
-                for (int jj = 0; jj < d; jj++) {
-                    const double dj = my[jj];
-                    const double *Arow = P.invcov + (size_t)jj * d;
-                    for (int k = 0; k < d; k++)
-                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
-                }
+            for (int jj = 0; jj < d; jj++) {
+                const double dj = my[jj];
+                const double *Arow = P.invcov + (size_t)jj * d;
+                for (int k = 0; k < d; k++)
+                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
             }
         }
         inside = valid && (acc <= P.r2);
@@ -223,8 +217,8 @@ __global__ void __launch_bounds__(128, prep_min_blocks(DR)) k_prep_reg(const Pre
             double dl[DR];
 #pragma unroll
             for (int k = 0; k < DR; k++) dl[k] = __dsub_rn(p[k], c_ell_center[k]);
-            // filter: r_fast = d^T (A d) with fused multiply-adds (d^2 + 2d DFMA instead of the
-            // einsum's 3 d^2 non-fused operations).  Both r_fast and the reference's sequential
+            // filter: r_fast = d^T (A d) with fused multiply-adds on the folded matrix
+            // (d(d+1)/2 + 2d DFMA instead of the einsum's 3 d^2 non-fused operations).  Both r_fast and the reference's sequential
             // einsum value lie within (d^2+2d+4) u * sum|d_j A_jk d_k| <= tol of d^T A d, with
             // sum|...| <= |d|^2 ||A||_F, so outside the band [r2 - tol, r2 + tol] the comparison
             // is already decided; inside the band the exact einsum order decides.
@@ -233,7 +227,7 @@ __global__ void __launch_bounds__(128, prep_min_blocks(DR)) k_prep_reg(const Pre
             for (int jj = 0; jj < DR; jj++) {
                 double y = 0.0;
 #pragma unroll
-                for (int k = 0; k < DR; k++) y = fma(c_ell_invcov[jj * DR + k], dl[k], y);
+                for (int k = jj; k < DR; k++) y = fma(c_ell_fold[jj * DR + k], dl[k], y);   // folded: k >= jj
                 rfast = fma(dl[jj], y, rfast);
                 nd = fma(dl[jj], dl[jj], nd);
             }
@@ -803,6 +797,12 @@ int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s)
     if (R.have_ellipsoid && R.ell_d == d) {
         UNB_TRY(upload_padded(ctx, c_ell_center, R.ell_center_h, 1, d, dr, s));
         UNB_TRY(upload_padded(ctx, c_ell_invcov, R.ell_invcov_h, d, d, dr, s));
+        std::vector<double> fold(d * d, 0.0);
+        for (size_t r = 0; r < d; r++) {
+            fold[r * d + r] = R.ell_invcov_h[r * d + r];
+            for (size_t c = r + 1; c < d; c++) fold[r * d + c] = R.ell_invcov_h[r * d + c] + R.ell_invcov_h[c * d + r];
+        }
+        UNB_TRY(upload_padded(ctx, c_ell_fold, fold, d, d, dr, s));
     }
     if (R.layer_kind == UNB_LAYER_AFFINE && R.layer_d == d) {
         UNB_TRY(upload_padded(ctx, c_xf_shift, R.layer_shift_h, 1, d, dr, s));
