@@ -3,10 +3,23 @@ every method is answered by the CPU oracle (oracle/cport.py).  Injected into
 ``ultranest_b200._native`` by the CPU tests so that the HOST logic of ``ultranest_b200/mlfriends.py``
 (RNG order, region/layer protocol, clustering loop, error types, the integrator drop-in) is
 exercised without a GPU.  It is never importable from the product package."""
+import ctypes
+
 import numpy as np
 
-from oracle import cport
+from oracle import cport, stepport
 from ultranest_b200 import _native
+
+
+def _view(ptr, shape, dtype):
+    """NumPy view of a caller-owned buffer passed as a raw address (what the C ABI receives)."""
+    if ptr is None:
+        return None
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.empty(shape, dtype=dtype)
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(int(ptr))
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 class OracleEngine(object):
@@ -186,3 +199,108 @@ class OracleEngine(object):
 
     def loglike_eggbox(self, z):
         return cport.loglike_eggbox(z)
+
+    # -- population step-sampler helpers: the C-ABI calls of ultranest_b200/stepfuncs.py and
+    #    popstepsampler.py, answered by oracle/stepport.py ----------------------------------
+    def call(self, name, *args):
+        self.calls += 1
+        return getattr(self, "_" + name)(*args)
+
+    def _desc(self, addr, ndim):
+        d = ctypes.cast(int(addr), ctypes.POINTER(_native.StepDesc)).contents
+        xform = None
+        if d.xform_kind == _native.XFORM_SCALE_SHIFT:
+            xform = (_view(d.xform_scale, (ndim,), np.float64).copy(), _view(d.xform_lo, (ndim,), np.float64).copy())
+        lparams = _view(d.lparams, (ndim + 2,), np.float64).copy() if d.lparams else None
+        kind = int(d.loglike_kind)
+        transform = (lambda u: u) if xform is None else (lambda u: u * xform[0] + xform[1])
+        return transform, (lambda v: self._like(np.ascontiguousarray(v), kind, lparams))
+
+    def _unb_within_unit_cube(self, u, n, d, acceptable):
+        _view(acceptable, (n,), bool)[:] = stepport.within_unit_cube(_view(u, (n, d), np.float64))
+
+    def _unb_evolve_prepare(self, sl, sr, n, search_right, bisecting):
+        a, b = stepport.evolve_prepare(_view(sl, (n,), bool), _view(sr, (n,), bool))
+        _view(search_right, (n,), bool)[:] = a
+        _view(bisecting, (n,), bool)[:] = b
+
+    def _unb_evolve_update(self, acceptable, Lnew, n_lnew, Lmin, search_right, bisecting, currentt,
+                           current_left, current_right, searching_left, searching_right, success, n):
+        f, b = np.float64, bool
+        stepport.evolve_update(_view(acceptable, (n,), b), _view(Lnew, (n_lnew,), f), Lmin,
+                               _view(search_right, (n,), b), _view(bisecting, (n,), b),
+                               _view(currentt, (n,), f), _view(current_left, (n,), f),
+                               _view(current_right, (n,), f), _view(searching_left, (n,), b),
+                               _view(searching_right, (n,), b), _view(success, (n,), b))
+
+    def _unb_evolve(self, desc, Lmin, currentu, currentv, currentt, current_left, current_right,
+                    searching_left, searching_right, n, ndim, acceptable, success, like):
+        """unb_evolve = stepfuncs.pyx:250-274 with the bisecting walkers' draws already in
+        currentt; restated from the oracle's pieces."""
+        f, b = np.float64, bool
+        transform, loglike = self._desc(desc, ndim)
+        u, v = _view(currentu, (n, ndim), f), _view(currentv, (n, ndim), f)
+        t, cl, cr = _view(currentt, (n,), f), _view(current_left, (n,), f), _view(current_right, (n,), f)
+        sl, sr = _view(searching_left, (n,), b), _view(searching_right, (n,), b)
+        search_right, bisecting = stepport.evolve_prepare(sl, sr)
+        coef = np.where(sl, cl, np.where(search_right, cr, t))
+        u[:] = u + v * coef.reshape((-1, 1))
+        acc = stepport.within_unit_cube(u)
+        L = np.full(n, -np.inf)
+        if acc.any():
+            L[acc] = loglike(transform(u[acc, :]))
+        succ = np.zeros(n, dtype=bool)
+        stepport.evolve_update(acc, L[acc], Lmin, search_right, bisecting, t, cl, cr, sl, sr, succ)
+        _view(acceptable, (n,), b)[:] = acc
+        _view(success, (n,), b)[:] = succ
+        _view(like, (n,), f)[:] = L
+
+    def _unb_step_back(self, Lmin, allL, nwalkers, ncols, generation, currentt):
+        if ncols > 2048:
+            raise ValueError("step_back supports chains of up to 2048 generations")
+        stepport.step_back(Lmin, _view(allL, (nwalkers, ncols), np.float64),
+                           _view(generation, (nwalkers,), np.int64), _view(currentt, (nwalkers,), np.float64))
+
+    def _unb_update_vectorised_slice_sampler(self, t, tleft, tright, pL, pu, pp, worker_running, status,
+                                             thr, shrink, allu, allL, allp, popsize, ndim, nparams,
+                                             discarded):
+        f, i = np.float64, np.int64
+        w = _view(worker_running, (popsize,), i)
+        if ((w < 0) | (w >= popsize)).any():
+            raise ValueError("worker_running outside the population")
+        out = stepport.update_vectorised_slice_sampler(
+            _view(t, (popsize,), f), _view(tleft, (popsize,), f), _view(tright, (popsize,), f),
+            _view(pL, (popsize,), f), _view(pu, (popsize, ndim), f), _view(pp, (popsize, nparams), f), w,
+            _view(status, (popsize,), i), thr, shrink, _view(allu, (popsize, ndim), f),
+            _view(allL, (popsize,), f), _view(allp, (popsize, nparams), f), popsize)
+        _view(discarded, (1,), i)[0] = out[-1]
+
+    def _unb_popslice_begin(self, desc, allu, allL, v, tleft, tright, popsize, ndim, thr, shrink):
+        f = np.float64
+        transform, loglike = self._desc(desc, ndim)
+        self._ps = dict(transform=transform, loglike=loglike, thr=thr, shrink=shrink,
+                        allu=_view(allu, (popsize, ndim), f).copy(), allL=_view(allL, (popsize,), f).copy(),
+                        v=_view(v, (popsize, ndim), f).copy(), tleft=_view(tleft, (popsize,), f).copy(),
+                        tright=_view(tright, (popsize,), f).copy(), allp=np.full((popsize, ndim), np.nan),
+                        worker=np.arange(popsize, dtype=np.int64), status=np.zeros(popsize, dtype=np.int64))
+        self._ps["tlw"], self._ps["trw"] = self._ps["tleft"].copy(), self._ps["tright"].copy()
+
+    def _unb_popslice_iterate(self, slice_position, n_running, discarded):
+        s = self._ps
+        n = len(s["allL"])
+        pos = _view(slice_position, (n,), np.float64)
+        s["tlw"], s["trw"], disc = stepport.popslice_iteration(
+            pos, s["tlw"], s["trw"], s["tleft"], s["tright"], s["worker"], s["status"], s["allu"], s["allL"],
+            s["allp"], s["v"], s["transform"], s["loglike"], s["thr"], s["shrink"])
+        n_running._obj.value = int((s["status"] == 0).sum())
+        discarded._obj.value = int(disc)
+
+    def _unb_popslice_end(self, allu, allp, allL, tleft, tright, status):
+        s = self._ps
+        n, d = s["allu"].shape
+        for ptr, key, shape, dt in ((allu, "allu", (n, d), np.float64), (allp, "allp", (n, d), np.float64),
+                                    (allL, "allL", (n,), np.float64), (tleft, "tleft", (n,), np.float64),
+                                    (tright, "tright", (n,), np.float64), (status, "status", (n,), np.int64)):
+            if ptr is not None:
+                _view(ptr, shape, dt)[...] = s[key]
+

@@ -68,3 +68,85 @@ def test_line_intersection_and_diagnostics(ref):
     np.testing.assert_array_equal(fa, fb)
     np.testing.assert_array_equal(ma, mb)
     assert ra == rb
+
+
+# ---- host logic of the device mirror with the kernels answered by the oracle -------------------
+
+@pytest.fixture()
+def stub_engine(monkeypatch):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from ultranest_b200 import _native
+    eng = OracleEngine()
+    monkeypatch.setattr(_native, "_engine", eng)
+    monkeypatch.setattr(_native, "get_engine", lambda: eng)
+    return eng
+
+
+def _device_callables(centre, sigma, lo=None, hi=None):
+    from ultranest_b200.likelihoods import GaussianLogLike
+    from ultranest_b200.transforms import IdentityTransform, ScaleShiftTransform
+    return (IdentityTransform() if lo is None else ScaleShiftTransform(lo, hi)), GaussianLogLike(centre, sigma)
+
+
+def test_mirror_matches_golden_through_the_stub(stub_engine):
+    """Argument marshalling, in-place contracts, RNG draw of the fused evolve, return shapes."""
+    import stepfuncs_cases as cases
+    import stepfuncs_checks as checks
+    from ultranest_b200 import stepfuncs as sf
+    g = checks.golden()
+    for check in checks.ALL_CHECKS:
+        if check is checks.check_evolve:
+            xf, ll = _device_callables(0.5, 0.1)
+            check(sf, g, xf, ll)                                             # fused entry point
+            check(sf, g, cases.identity, cases.gauss_loglike(0.5, 0.1))      # staged around host callables
+        else:
+            check(sf, g)
+    assert stub_engine.calls > 10
+
+
+def test_sampler_runs_are_the_reference_runs_through_the_stub(stub_engine, ref):
+    """PopulationSliceSampler on the installed helpers and PopulationSimpleSliceSampler on the
+    device loop return the reference's points (host logic only; the GPU tier repeats this with
+    the real kernels)."""
+    import test_gpu_stepfuncs as G
+    import stepfuncs_cases as cases
+    from ultranest_b200 import popstepsampler as pp
+    from ultranest_b200 import stepfuncs as sf
+    rs, rp = ref
+    d = 4
+    region = _region(8, 300, d)
+    region.transformLayer.transform = lambda x: x * 3.0
+    us = region.u
+    host_ll = cases.gauss_loglike(0.5, 0.15)
+    Ls = host_ll(us)
+    make = lambda: rp.PopulationSliceSampler(popsize=30, nsteps=5, generate_direction=rs.generate_mixture_random_direction)  # noqa: E731
+    want = G._harvest(make(), region, us, Ls, cases.identity, host_ll, 20, 21)
+    xf, ll = _device_callables(0.5, 0.15)
+    undo = sf.install()
+    try:
+        got = G._harvest(make(), region, us, Ls, xf, ll, 20, 21)
+    finally:
+        sf.uninstall(undo)
+    for (u, p, L, nc), (u2, p2, L2, nc2) in zip(got, want):
+        np.testing.assert_array_equal(u, u2)
+        np.testing.assert_array_equal(p, p2)
+        assert L == L2 and nc == nc2
+    lo, hi = np.full(d, -1.0), np.full(d, 2.0)
+    host_xf = lambda x: x * (hi - lo) + lo   # noqa: E731
+    host_ll = cases.gauss_loglike(0.5, 0.5)
+    Ls = host_ll(host_xf(us))
+    kw = dict(popsize=64, nsteps=4, generate_direction=rs.generate_region_random_direction, shrink_factor=1.2)
+    want = G._harvest(rp.PopulationSimpleSliceSampler(**kw), region, us, Ls, host_xf, host_ll, 100, 31, np.min)
+    xf, ll = _device_callables(0.5, 0.5, lo, hi)
+    sampler = rp.PopulationSimpleSliceSampler(**kw)
+    stats = pp.attach(sampler)
+    got = G._harvest(sampler, region, us, Ls, xf, ll, 100, 31, np.min)
+    assert stats["fused_calls"] > 0 and stats["delegated_calls"] == 0
+    for (u, p, L, nc), (u2, p2, L2, nc2) in zip(got, want):
+        np.testing.assert_array_equal(u, u2)
+        np.testing.assert_array_equal(p, p2)
+        assert L == L2 and nc == nc2
+    assert sampler.ncalls > 0

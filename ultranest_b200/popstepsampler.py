@@ -85,60 +85,73 @@ class SliceLoop(object):
         return allu, allp, allL, tleft, tright, status
 
 
+def _slice_move(sampler, loop, region, Lmin, allu, allL, allp):
+    """One of the ``nsteps`` slice moves of the whole population (popstepsampler.py:913-968):
+    direction and limits on the host, the pass loop on the device.  Returns the moved population,
+    the likelihood calls spent, the discarded evaluations and the median final slice width."""
+    jitter = sampler.scale_jitter_func()
+    v = sampler.generate_direction(allu, region, scale=1.0) * sampler.scale * jitter
+    cube_lo, cube_hi = unitcube_line_intersection(allu, v)
+    # the reference derives the per-worker and the per-point limits by two identical calls
+    # (:926-929); workers start on their own point, so the second pair serves both
+    sampler.slice_limit(cube_lo, cube_hi)
+    tleft, tright = sampler.slice_limit(cube_lo, cube_hi)
+    loop.begin(allu, allL, v, tleft, tright, Lmin, sampler.shrink_factor)
+    ncalls = ndiscarded = 0
+    for _ in range(sampler.max_it):
+        n_running, n_disc = loop.iterate(np.random.uniform(size=(sampler.popsize,)))
+        ncalls += sampler.popsize
+        ndiscarded += n_disc
+        if n_running == 0:
+            break
+    allu, moved_p, allL, tleft, tright, status = loop.end()
+    moved = status == 1
+    allp[moved, :] = moved_p[moved, :]
+    return allu, allL, allp, ncalls, ndiscarded, np.median(tright - tleft)
+
+
+def _refill_pool(sampler, region, Lmin, us, Ls, transform, loglike, test):
+    """Refill ``prepared_samples`` (popstepsampler.py:901-1000): same RNG consumption, counters,
+    diagnostics and scale adaptation as the reference; returns the likelihood calls spent."""
+    nlive, ndim = us.shape
+    ilive = np.random.randint(0, nlive, size=sampler.popsize)
+    allu = np.array(us) if test else np.array(us[ilive, :])
+    allp = np.full((sampler.popsize, ndim), np.nan)
+    allL = np.array(Ls[ilive])
+    loop = SliceLoop(transform, loglike, ndim)
+    nc = n_discarded = 0
+    width_sum = 0.
+    for _ in range(sampler.nsteps):
+        allu, allL, allp, dc, dd, width = _slice_move(sampler, loop, region, Lmin, allu, allL, allp)
+        nc += dc
+        n_discarded += dd
+        width_sum += width
+    mean_width = width_sum / sampler.nsteps
+    sampler.discarded += n_discarded
+    sampler.ncalls += nc
+    assert np.isfinite(allp).all(), 'some walkers never moved! Double nsteps of PopulationSimpleSliceSampler.'
+    far_enough, (moved_by, radius) = diagnose_move_distances(region, us[ilive, :], allu)
+    sampler.prepared_samples = list(zip(allu, allp, allL))
+    have = len(far_enough) > 0
+    sampler.logstat.append([
+        sampler.popsize / nc, sampler.scale, sampler.nsteps,
+        np.mean(far_enough) if have else 0,
+        np.exp(np.mean(np.log(moved_by / radius + 1e-10))) if have else 0])
+    # widen the slice when the final intervals stay long, shrink it otherwise (:994-998)
+    if mean_width >= 1. / sampler.adapt_slice_scale_target:
+        sampler.scale *= 1. / sampler.scale_adapt_factor
+    else:
+        sampler.scale *= sampler.scale_adapt_factor
+    return nc
+
+
 def fused_next(self, region, Lmin, us, Ls, transform, loglike, ndraw=10, plot=False, tregion=None,
                log=False, test=False):
     """``PopulationSimpleSliceSampler.__next__`` (popstepsampler.py:863-1001) with the pass loop
     on the device.  Same return value, RNG consumption, counters and adaptation."""
-    nlive, ndim = us.shape
+    nc = 0
     if len(self.prepared_samples) == 0:
-        ilive = np.random.randint(0, nlive, size=self.popsize)
-        allu = np.array(us[ilive, :]) if not test else np.array(us)
-        allp = np.zeros((self.popsize, ndim)) * np.nan
-        allL = np.array(Ls[ilive])
-        nc = 0
-        n_discarded = 0
-        interval_final = 0.
-        loop = SliceLoop(transform, loglike, ndim)
-        for _k in range(self.nsteps):
-            factor_scale = self.scale_jitter_func()
-            v = self.generate_direction(allu, region, scale=1.0) * self.scale * factor_scale
-            tleft_unitcube, tright_unitcube = unitcube_line_intersection(allu, v)
-            # the reference derives the per-worker and the per-point limits by two identical
-            # calls (:926-929); workers start on their own point, so one pair serves both
-            self.slice_limit(tleft_unitcube, tright_unitcube)
-            tleft, tright = self.slice_limit(tleft_unitcube, tright_unitcube)
-            loop.begin(allu, allL, v, tleft, tright, Lmin, self.shrink_factor)
-            for _it in range(self.max_it):
-                slice_position = np.random.uniform(size=(self.popsize,))
-                n_running, n_discarded_it = loop.iterate(slice_position)
-                nc += self.popsize
-                n_discarded += n_discarded_it
-                if n_running == 0:
-                    break
-            allu, allp_step, allL, tleft, tright, status = loop.end()
-            moved = status == 1
-            allp[moved, :] = allp_step[moved, :]
-            interval_final += np.median(tright - tleft)
-
-        interval_final = interval_final / self.nsteps
-        self.discarded += n_discarded
-        self.ncalls += nc
-        assert np.isfinite(allp).all(), 'some walkers never moved! Double nsteps of PopulationSimpleSliceSampler.'
-        far_enough, (move_distance, reference_distance) = diagnose_move_distances(region, us[ilive, :], allu)
-        self.prepared_samples = list(zip(allu, allp, allL))
-        self.logstat.append([
-            self.popsize / nc,
-            self.scale,
-            self.nsteps,
-            np.mean(far_enough) if len(far_enough) > 0 else 0,
-            np.exp(np.mean(np.log(move_distance / reference_distance + 1e-10))) if len(far_enough) > 0 else 0
-        ])
-        if interval_final >= 1. / self.adapt_slice_scale_target:
-            self.scale *= 1. / self.scale_adapt_factor
-        else:
-            self.scale *= self.scale_adapt_factor
-    else:
-        nc = 0
+        nc = _refill_pool(self, region, Lmin, us, Ls, transform, loglike, test)
     u, p, L = self.prepared_samples.pop(0)
     return u, p, L, nc
 
