@@ -772,13 +772,27 @@ size_t unb_max_rowwise_d() { return ROW_SMEM_BUDGET / sizeof(double) / 32 - 1; }
 static const unb_ctx *g_const_owner = nullptr;
 static long long g_const_version = -1;
 
-static int upload_padded(unb_ctx *ctx, const void *symbol, const std::vector<double> &src,
-                         size_t rows, size_t cols, size_t stride, cudaStream_t s)
+// what the constant block currently holds (zero-padded images), so that a call re-sends only the
+// arrays that changed: the integrator moves the ellipsoid centre every iteration
+// (integrator.py:2756) but the matrices only at a region rebuild
+static std::vector<double> g_img_center, g_img_invcov, g_img_shift, g_img_mat;
+
+static std::vector<double> padded_image(const std::vector<double> &src, size_t rows, size_t cols, size_t stride)
 {
     std::vector<double> buf(rows * stride, 0.0);
     for (size_t r = 0; r < rows; r++)
         for (size_t c = 0; c < cols; c++) buf[r * stride + c] = src[r * cols + c];
-    UNB_CUDA(ctx, cudaMemcpyToSymbolAsync(symbol, buf.data(), buf.size() * sizeof(double), 0,
+    return buf;
+}
+
+static bool same_image(const std::vector<double> &a, const std::vector<double> &b)
+{
+    return a.size() == b.size() && (a.empty() || memcmp(a.data(), b.data(), a.size() * sizeof(double)) == 0);
+}
+
+static int send_image(unb_ctx *ctx, const void *symbol, const std::vector<double> &img, cudaStream_t s)
+{
+    UNB_CUDA(ctx, cudaMemcpyToSymbolAsync(symbol, img.data(), img.size() * sizeof(double), 0,
                                           cudaMemcpyHostToDevice, s));
     return UNB_OK;
 }
@@ -791,30 +805,50 @@ int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s)
     const size_t d = R.have_ellipsoid ? R.ell_d : R.live.d;
     if (d > (size_t)CONST_MAXD) return UNB_OK;
     const size_t dr = (d + 3) / 4 * 4;
-    // kernels of either lane may still read the old values
-    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
-    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+    if (g_const_owner != ctx) {
+        g_img_center.clear(); g_img_invcov.clear(); g_img_shift.clear(); g_img_mat.clear();
+    }
+    std::vector<double> center, invcov, shift, mat;
     if (R.have_ellipsoid && R.ell_d == d) {
-        UNB_TRY(upload_padded(ctx, c_ell_center, R.ell_center_h, 1, d, dr, s));
-        UNB_TRY(upload_padded(ctx, c_ell_invcov, R.ell_invcov_h, d, d, dr, s));
-        std::vector<double> fold(d * d, 0.0);
-        for (size_t r = 0; r < d; r++) {
-            fold[r * d + r] = R.ell_invcov_h[r * d + r];
-            for (size_t c = r + 1; c < d; c++) fold[r * d + c] = R.ell_invcov_h[r * d + c] + R.ell_invcov_h[c * d + r];
-        }
-        UNB_TRY(upload_padded(ctx, c_ell_fold, fold, d, d, dr, s));
+        center = padded_image(R.ell_center_h, 1, d, dr);
+        invcov = padded_image(R.ell_invcov_h, d, d, dr);
     }
     if (R.layer_kind == UNB_LAYER_AFFINE && R.layer_d == d) {
-        UNB_TRY(upload_padded(ctx, c_xf_shift, R.layer_shift_h, 1, d, dr, s));
-        UNB_TRY(upload_padded(ctx, c_xf_mat, R.layer_mat_h, d, d, dr, s));
+        shift = padded_image(R.layer_shift_h, 1, d, dr);
+        mat = padded_image(R.layer_mat_h, d, d, dr);
     } else if (R.layer_kind == UNB_LAYER_SCALING && R.layer_d == d) {
-        UNB_TRY(upload_padded(ctx, c_xf_shift, R.layer_shift_h, 1, d, dr, s));
-        std::vector<double> ones(dr, 1.0);
-        for (size_t k = 0; k < d; k++) ones[k] = R.layer_mat_h[k];
-        UNB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_xf_mat, ones.data(), dr * sizeof(double), 0,
-                                              cudaMemcpyHostToDevice, s));
+        shift = padded_image(R.layer_shift_h, 1, d, dr);
+        mat.assign(dr, 1.0);
+        for (size_t k = 0; k < d; k++) mat[k] = R.layer_mat_h[k];
     }
-    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    const bool new_center = !center.empty() && !same_image(center, g_img_center);
+    const bool new_invcov = !invcov.empty() && !same_image(invcov, g_img_invcov);
+    const bool new_shift = !shift.empty() && !same_image(shift, g_img_shift);
+    const bool new_mat = !mat.empty() && !same_image(mat, g_img_mat);
+    if (new_center || new_invcov || new_shift || new_mat) {
+        // kernels of either lane may still read the old values
+        UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
+        UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+        std::vector<double> fold;
+        if (new_center) UNB_TRY(send_image(ctx, c_ell_center, center, s));
+        if (new_invcov) {
+            UNB_TRY(send_image(ctx, c_ell_invcov, invcov, s));
+            fold.assign(d * dr, 0.0);
+            for (size_t r = 0; r < d; r++) {
+                fold[r * dr + r] = R.ell_invcov_h[r * d + r];
+                for (size_t c = r + 1; c < d; c++)
+                    fold[r * dr + c] = R.ell_invcov_h[r * d + c] + R.ell_invcov_h[c * d + r];
+            }
+            UNB_TRY(send_image(ctx, c_ell_fold, fold, s));
+        }
+        if (new_shift) UNB_TRY(send_image(ctx, c_xf_shift, shift, s));
+        if (new_mat) UNB_TRY(send_image(ctx, c_xf_mat, mat, s));
+        UNB_CUDA(ctx, cudaStreamSynchronize(s));   // the images are read from pageable memory
+        if (new_center) g_img_center.swap(center);
+        if (new_invcov) g_img_invcov.swap(invcov);
+        if (new_shift) g_img_shift.swap(shift);
+        if (new_mat) g_img_mat.swap(mat);
+    }
     g_const_owner = ctx;
     g_const_version = R.param_version;
     return UNB_OK;
