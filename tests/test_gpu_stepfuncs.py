@@ -204,6 +204,27 @@ def test_simple_slice_sampler_device_loop_is_the_reference_run(shrink, scale):
         np.testing.assert_array_equal(u, u2)
 
 
+def test_evolve_in_chunks(sf):
+    """Large populations pass through unb_evolve in chunks of walkers; forced here with a tiny chunk."""
+    from ultranest_b200 import _native
+    xf, ll = _device_callables(0.5, 0.1)
+    a, b = cases.evolve_state(9, 2000, 7), cases.evolve_state(9, 2000, 7)
+    np.random.seed(3)
+    ra = sf.evolve(xf, ll, -8.0, **a)
+    eng = _native.get_engine()
+    eng.set_option(_native.OPT_CHUNK_ROWS, 333)
+    try:
+        np.random.seed(3)
+        rb = sf.evolve(xf, ll, -8.0, **b)
+    finally:
+        eng.set_option(_native.OPT_CHUNK_ROWS, 0)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    for x, y in zip(ra[1], rb[1]):
+        np.testing.assert_array_equal(x, y)
+    assert ra[2] == rb[2]
+
+
 def test_argument_errors(sf):
     with pytest.raises(ValueError):
         sf.step_back(0.0, np.zeros((3, 4000)), np.zeros(3, dtype=np.int64), np.zeros(3))

@@ -579,28 +579,18 @@ extern "C" int unb_evolve_update(unb_ctx *ctx, const uint8_t *acceptable, const 
     return UNB_OK;
 }
 
-extern "C" int unb_evolve(unb_ctx *ctx, const unb_step_desc *desc, double Lmin, double *currentu,
-                          const double *currentv, double *currentt, double *current_left,
-                          double *current_right, uint8_t *searching_left, uint8_t *searching_right,
-                          size_t n, size_t ndim, uint8_t *acceptable, uint8_t *success, double *like)
+namespace {
+
+// one chunk of walkers through the fused evolve kernel.  One device blob, laid out
+//   [v | u t left right sl sr | like acceptable success]
+// so that the upload is the first two groups and the download the last two, each ONE copy through
+// pinned staging (a step moves nine small arrays; nine pageable copies cost more than the kernel).
+int evolve_chunk(unb_ctx *ctx, EvolveArgs A, int threads, double *currentu, const double *currentv,
+                 double *currentt, double *current_left, double *current_right,
+                 uint8_t *searching_left, uint8_t *searching_right, size_t n, size_t ndim,
+                 uint8_t *acceptable, uint8_t *success, double *like, cudaStream_t s)
 {
-    UNB_TRY(check(ctx));
-    ctx->ps_active = false;   // the scratch buffers are shared with the slice-loop session
-    if (n == 0) return UNB_OK;
-    if (!desc || !currentu || !currentv || !currentt || !current_left || !current_right ||
-        !searching_left || !searching_right || !acceptable || !success || !like || ndim == 0)
-        return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
-    const int threads = row_threads_for(2 * sf_odd((int)ndim));
-    if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%zu too large for the row kernels", ndim);
-    cudaStream_t s = S0(ctx);
-    EvolveArgs A;
-    memset(&A, 0, sizeof(A));
-    UNB_TRY(upload_desc(ctx, desc->xform_kind, desc->xform_scale, desc->xform_lo, desc->loglike_kind,
-                        desc->lparams, ndim, s, &A.xform_scale, &A.xform_lo, &A.lparams));
     const size_t nb = n * sizeof(double), rb = n * ndim * sizeof(double);
-    // One device blob, laid out  [v | u t left right sl sr | like acceptable success]  so that the
-    // upload is the first two groups and the download the last two, each ONE copy through pinned
-    // staging (a step moves nine small arrays; nine pageable copies cost more than the kernel).
     auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t o_v = 0, o_u = o_v + al(rb), o_t = o_u + al(rb), o_l = o_t + al(nb), o_r = o_l + al(nb),
                  o_sl = o_r + al(nb), o_sr = o_sl + al(n), o_like = o_sr + al(n), o_acc = o_like + al(nb),
@@ -628,10 +618,6 @@ extern "C" int unb_evolve(unb_ctx *ctx, const unb_step_desc *desc, double Lmin, 
     A.acceptable = (unsigned char *)(dev + o_acc);
     A.success = (unsigned char *)(dev + o_succ);
     A.n = (long long)n;
-    A.d = (int)ndim;
-    A.xform_kind = desc->xform_kind;
-    A.loglike_kind = desc->loglike_kind;
-    A.Lmin = Lmin;
     const size_t smem = (size_t)threads * 2 * sf_odd((int)ndim) * sizeof(double);
     UNB_TRY(allow_smem(ctx, k_evolve_fused, smem));
     k_evolve_fused<<<blocks_for(n, threads), threads, smem, s>>>(A);
@@ -649,6 +635,45 @@ extern "C" int unb_evolve(unb_ctx *ctx, const unb_step_desc *desc, double Lmin, 
     memcpy(like, pin + o_like, nb);
     memcpy(acceptable, pin + o_acc, n);
     memcpy(success, pin + o_succ, n);
+    return UNB_OK;
+}
+
+}  // namespace
+
+extern "C" int unb_evolve(unb_ctx *ctx, const unb_step_desc *desc, double Lmin, double *currentu,
+                          const double *currentv, double *currentt, double *current_left,
+                          double *current_right, uint8_t *searching_left, uint8_t *searching_right,
+                          size_t n, size_t ndim, uint8_t *acceptable, uint8_t *success, double *like)
+{
+    UNB_TRY(check(ctx));
+    ctx->ps_active = false;   // the scratch buffers are shared with the slice-loop session
+    if (n == 0) return UNB_OK;
+    if (!desc || !currentu || !currentv || !currentt || !current_left || !current_right ||
+        !searching_left || !searching_right || !acceptable || !success || !like || ndim == 0)
+        return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    const int threads = row_threads_for(2 * sf_odd((int)ndim));
+    if (threads < 32) return unb_fail(ctx, UNB_ERR_ARG, "ndim=%zu too large for the row kernels", ndim);
+    cudaStream_t s = S0(ctx);
+    EvolveArgs A;
+    memset(&A, 0, sizeof(A));
+    UNB_TRY(upload_desc(ctx, desc->xform_kind, desc->xform_scale, desc->xform_lo, desc->loglike_kind,
+                        desc->lparams, ndim, s, &A.xform_scale, &A.xform_lo, &A.lparams));
+    A.d = (int)ndim;
+    A.xform_kind = desc->xform_kind;
+    A.loglike_kind = desc->loglike_kind;
+    A.Lmin = Lmin;
+    // walkers are independent: large populations go through in chunks that keep the pinned staging
+    // blob around 32 MB (UNB_OPT_CHUNK_ROWS overrides the chunk length, for tests)
+    size_t chunk = (32u << 20) / ((2 * ndim + 4) * sizeof(double) + 4);
+    if (ctx->chunk_rows > 0) chunk = (size_t)ctx->chunk_rows;
+    if (chunk < 1) chunk = 1;
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t cn = n - off < chunk ? n - off : chunk;
+        UNB_TRY(evolve_chunk(ctx, A, threads, currentu + off * ndim, currentv + off * ndim, currentt + off,
+                             current_left + off, current_right + off, searching_left + off,
+                             searching_right + off, cn, ndim, acceptable + off, success + off,
+                             like + off, s));
+    }
     return UNB_OK;
 }
 
