@@ -150,3 +150,31 @@ def test_sampler_runs_are_the_reference_runs_through_the_stub(stub_engine, ref):
         np.testing.assert_array_equal(p, p2)
         assert L == L2 and nc == nc2
     assert sampler.ncalls > 0
+
+
+def test_package_install_rebinds_step_helpers(stub_engine, ref):
+    """ultranest_b200.install(stepfuncs=True) swaps the names popstepsampler imported;
+    uninstall_stepfuncs() restores them.  (The region half of install() is exercised, with full
+    save/restore of the integrator's bindings, by tests/test_host_logic_cpu.py.)"""
+    import sys
+    import ultranest_b200
+    from ultranest_b200 import stepfuncs as sf
+    rs, rp = ref
+    region_too = "ultranest.integrator" not in sys.modules   # else install() would need force=True
+    saved_mod = sys.modules.get("ultranest.mlfriends")
+    saved_attr = getattr(sys.modules["ultranest"], "mlfriends", None)
+    before = {n: getattr(rp, n) for n in sf._NAMES if hasattr(rp, n)}
+    try:
+        if region_too:
+            ultranest_b200.install(stepfuncs=True)
+        else:
+            ultranest_b200._step_undo.extend(sf.install())
+        assert rp.evolve is sf.evolve and rp.step_back is sf.step_back
+        assert rs.update_vectorised_slice_sampler is sf.update_vectorised_slice_sampler
+    finally:
+        ultranest_b200.uninstall_stepfuncs()
+        if saved_mod is not None:
+            sys.modules["ultranest.mlfriends"] = saved_mod
+            sys.modules["ultranest"].mlfriends = saved_attr
+    for n, fn in before.items():
+        assert getattr(rp, n) is fn

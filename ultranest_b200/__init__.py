@@ -14,14 +14,24 @@ Use it from an unmodified UltraNest either per run::
 or process-wide, before ``ultranest.integrator`` is imported::
 
     import ultranest_b200; ultranest_b200.install()
+
+Beyond the region: :mod:`ultranest_b200.refill` fuses ``_refill_samples`` into one device pipeline
+(``refill.attach(sampler)``), :mod:`ultranest_b200.stepfuncs` / :mod:`ultranest_b200.popstepsampler`
+put the compiled helpers of the population step samplers (``ultranest/stepfuncs.pyx``) and the
+inner loop of ``PopulationSimpleSliceSampler`` on the device (``install(stepfuncs=True)``,
+``popstepsampler.attach(stepsampler)``).
 """
 import sys
 
 __version__ = "0.1.0"
 
 
-def install(force=False):
+def install(force=False, stepfuncs=False):
     """Make ``import ultranest.mlfriends`` resolve to :mod:`ultranest_b200.mlfriends`.
+
+    ``stepfuncs=True`` also rebinds the step-sampler helpers ``ultranest.popstepsampler`` imported
+    by name (``evolve``, ``step_back``, ``update_vectorised_slice_sampler``, the direction
+    generators; :func:`ultranest_b200.stepfuncs.install`).
 
     ``ultranest/integrator.py`` binds ``MLFriends``, ``AffineLayer``, ``WrappingEllipsoid``,
     ``find_nearby`` ... by name at import time (integrator.py:28-30), so this must run before
@@ -51,4 +61,17 @@ def install(force=False):
                 defaults = getattr(fn, "__defaults__", None)
                 if defaults and any(id(v) in replaced for v in defaults):
                     fn.__defaults__ = tuple(replaced.get(id(v), v) for v in defaults)
+    if stepfuncs:
+        from . import stepfuncs as ours_steps
+        _step_undo.extend(ours_steps.install())
     return ours
+
+
+_step_undo = []
+
+
+def uninstall_stepfuncs():
+    """Put back the reference's step-sampler helpers replaced by ``install(stepfuncs=True)``."""
+    from . import stepfuncs as ours_steps
+    ours_steps.uninstall(_step_undo)
+    del _step_undo[:]
