@@ -35,6 +35,9 @@ NDIM = 20
 SIGMA = 0.01
 NBOOT = 30
 METRIC = "proposed-points/sec through MLFriends.inside + loglike, N_live=4000 d=20"
+# the same workload description on both arms (ours and --impl reference)
+WORKLOAD = ("BASELINE configs[1]: 20-D correlated Gaussian live set, N_live=4000, AffineLayer, "
+            "MLFriends.inside() + Gaussian loglike, wrapping-ellipsoid proposals (accepting regime)")
 
 
 # --------------------------------------------------------------------------------------
@@ -249,9 +252,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "20-D correlated Gaussian live set, N_live=4000, AffineLayer, "
-                               "MLFriends inside() + Gaussian loglike, wrapping-ellipsoid proposals",
-                   "rows_per_step": base["rows"], "n_live": N_LIVE, "ndim": NDIM},
+        "config": {"workload": WORKLOAD, "rows_per_step": base["rows"], "n_live": N_LIVE, "ndim": NDIM,
+                   "sample": base["sample"]},
         "cpu_baseline": {"value": base["value"], "unit": "points/s", "cores": base["cores"],
                          "kind": base["kind"], "sample": base["sample"]},
         "e2e": {"value": base["value"], "unit": "points/s", "h2d_bytes_per_step": 0,
@@ -485,9 +487,7 @@ def run_ours(args):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: 20-D correlated Gaussian live set, N_live=4000, "
-                               "AffineLayer, MLFriends.inside() + Gaussian loglike, "
-                               "wrapping-ellipsoid proposals (accepting regime)",
+        "config": {"workload": WORKLOAD,
                    "rows_per_step_per_gpu": M, "n_live": N_LIVE, "ndim": NDIM,
                    "l2_policy": "inputs larger than L2 (%.0f MB of proposals per step)" % (M * NDIM * 8 / 1e6),
                    "parallelism": "proposal rows sharded over %d GPU(s), no data-path collective" % world,
