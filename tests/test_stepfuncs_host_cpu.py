@@ -178,3 +178,33 @@ def test_package_install_rebinds_step_helpers(stub_engine, ref):
             sys.modules["ultranest"].mlfriends = saved_attr
     for n, fn in before.items():
         assert getattr(rp, n) is fn
+
+
+def test_integrator_run_with_attached_step_sampler(stub_engine, ref):
+    """The unmodified ReactiveNestedSampler driving a PopulationSimpleSliceSampler whose inner
+    loop is attached to the device path (here: the oracle stub) makes the reference's run --
+    attach() has to survive the integrator's keyword-argument call (integrator.py:1896-1900)."""
+    from ultranest import ReactiveNestedSampler
+    from ultranest_b200 import popstepsampler as pp
+    from ultranest_b200.likelihoods import GaussianLogLike
+    from ultranest_b200.transforms import IdentityTransform
+    rs, rp = ref
+    d, sigma = 3, 0.1
+
+    def numpy_loglike(theta):
+        return -0.5 * (((theta - 0.5) / sigma)**2).sum(axis=1) - 0.5 * np.log(2 * np.pi * sigma**2) * d
+
+    def run(loglike, transform, attach):
+        np.random.seed(5)
+        sampler = ReactiveNestedSampler(["a", "b", "c"], loglike, transform=transform, log_dir=None,
+                                        vectorized=True)
+        sampler.stepsampler = rp.PopulationSimpleSliceSampler(
+            popsize=40, nsteps=4, generate_direction=rs.generate_mixture_random_direction)
+        stats = pp.attach(sampler.stepsampler) if attach else None
+        res = sampler.run(min_num_live_points=100, max_ncalls=6000, viz_callback=False, show_status=False)
+        return res["logz"], res["ncall"], res["niter"], stats
+
+    want = run(numpy_loglike, lambda x: x, False)
+    got = run(GaussianLogLike(0.5, sigma), IdentityTransform(), True)
+    assert got[3]["fused_calls"] > 0 and got[3]["delegated_calls"] == 0
+    assert got[:3] == want[:3]
