@@ -208,3 +208,32 @@ def test_integrator_run_with_attached_step_sampler(stub_engine, ref):
     got = run(GaussianLogLike(0.5, sigma), IdentityTransform(), True)
     assert got[3]["fused_calls"] > 0 and got[3]["delegated_calls"] == 0
     assert got[:3] == want[:3]
+
+
+def test_mirror_rejects_unusable_buffers_before_any_device_call(stub_engine):
+    """The reference writes through typed memoryviews and raises on a wrong dtype / layout; the
+    mirror must refuse the same inputs instead of silently working on a copy."""
+    from ultranest_b200 import stepfuncs as sf
+    calls = stub_engine.calls
+    f = np.zeros(4)
+    b = np.zeros(4, dtype=bool)
+    with pytest.raises(ValueError):    # float32 state
+        sf.evolve_update(b, f[:0], 0.0, b, b, np.zeros(4, dtype=np.float32), f.copy(), f.copy(),
+                         b.copy(), b.copy(), b.copy())
+    with pytest.raises(ValueError):    # non-contiguous in/out array
+        sf.evolve_update(b, f[:0], 0.0, b, b, np.zeros(8)[::2], f.copy(), f.copy(), b.copy(), b.copy(), b.copy())
+    with pytest.raises(ValueError):    # int flags
+        sf.evolve_prepare(np.zeros(4, dtype=np.int64), b)
+    with pytest.raises(ValueError):    # generation must be int64
+        sf.step_back(0.0, np.zeros((4, 3)), np.zeros(4, dtype=np.int32), f.copy())
+    with pytest.raises(ValueError):    # arrays shorter than popsize
+        sf.update_vectorised_slice_sampler(f, f.copy(), f.copy(), f, np.zeros((4, 2)), np.zeros((4, 2)),
+                                           np.arange(4, dtype=np.int64), np.zeros(4, dtype=np.int64), 0.0, 1.0,
+                                           np.zeros((4, 2)), f.copy(), np.zeros((4, 2)), 5)
+    assert stub_engine.calls == calls
+    # empty populations are fine and touch nothing
+    e = np.empty(0)
+    eb = np.empty(0, dtype=bool)
+    assert sf.within_unit_cube(np.empty((0, 3))).shape == (0,)
+    sf.evolve_update(eb, e, 0.0, eb, eb, e.copy(), e.copy(), e.copy(), eb.copy(), eb.copy(), eb.copy())
+    sf.step_back(0.0, np.empty((0, 4)), np.empty(0, dtype=np.int64), e.copy())
