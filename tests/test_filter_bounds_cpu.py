@@ -168,3 +168,31 @@ def test_fp64_filter_never_loses_a_neighbour(d, scale, offset, r2rel):
     flagged = _hi32(acc) >= _hi32(thr) - 1
     assert 0.1 < hit.mean() < 0.9
     assert flagged[hit].all()
+
+
+@pytest.mark.parametrize("d", [2, 5, 20, 32, 50, 100, 143])
+@pytest.mark.parametrize("cond", [1e0, 1e6, 1e12])
+def test_ellipsoid_filter_band_covers_the_einsum_value(d, cond):
+    """Prep kernels (k_prep_reg, k_prep_tile): the fused filter value on the FOLDED matrix
+    (S_jj = A_jj, S_jk = A_jk + A_kj above the diagonal) and the reference's einsum value
+    (acc += (d_j A_jk) d_k, mlfriends.pyx:910) differ by less than the band half-width
+    tol = 2 (d^2 + 2d + 8) u |A|_F |delta|^2, so deciding rows outside the band by the filter and
+    rows inside it by the exact order gives the reference's mask -- also for ill-conditioned A."""
+    from oracle import cport
+    rng = np.random.RandomState(d + int(np.log10(cond)))
+    n = 3000
+    q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    eig = np.logspace(0, np.log10(cond), d)
+    cov = (q * eig) @ q.T
+    A = np.linalg.inv(cov)                      # not exactly symmetric, like the reference's invcov
+    ctr = rng.uniform(0.4, 0.6, size=d)
+    pts = ctr + rng.normal(size=(n, d)) * np.sqrt(eig.mean())
+    _, r_ref = cport.inside_ellipsoid(pts, ctr, A, 1.0, return_r=True)
+    delta = pts - ctr
+    S = np.triu(A, 1) + np.triu(A.T, 1) + np.diag(np.diag(A))
+    r_fast = np.einsum('ij,ij->i', delta @ S.T, delta)     # sum_j d_j sum_{k>=j} S_jk d_k
+    tol = 2.0 * (d * d + 2 * d + 8) * 2.0**-53 * np.sqrt((A * A).sum()) * (delta**2).sum(axis=1)
+    assert (np.abs(r_fast - r_ref) <= 0.5 * tol).all()
+    # the band is a sliver of the value range unless A is nearly singular
+    if cond <= 1e6:
+        assert np.median(tol / np.abs(r_ref)) < 1e-6
