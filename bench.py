@@ -40,6 +40,37 @@ WORKLOAD = ("BASELINE configs[1]: 20-D correlated Gaussian live set, N_live=4000
             "MLFriends.inside() + Gaussian loglike, wrapping-ellipsoid proposals (accepting regime)")
 
 
+def workload_config(world, batch):
+    """The `config` object: identical on both arms (ours and --impl reference) by construction.
+    The reference arm times a bounded sample of this workload (see its `cpu_baseline.sample`)."""
+    return {"workload": WORKLOAD, "n_live": N_LIVE, "ndim": NDIM, "nbootstraps": NBOOT,
+            "rows_per_step_per_gpu": int(batch),
+            "l2_policy": "inputs larger than L2 (%.0f MB of proposals per step per GPU)" % (batch * NDIM * 8 / 1e6),
+            "parallelism": "proposal rows sharded over %d GPU(s), no data-path collective; bootstrap "
+                           "rounds sharded with one allreduce(MAX) per rebuild" % world}
+
+
+def multimodal_live(n=2000, d=10, seed=5):
+    """Eggbox-like live set (BASELINE configs[2] shape: N=2000, d=10): points around a lattice of
+    modes, as a seeded eggbox run leaves them at a rebuild with many clusters."""
+    rng = np.random.RandomState(seed)
+    centres = rng.randint(0, 5, size=(n, d)) * 0.2 + 0.1
+    return centres + rng.normal(size=(n, d)) * 0.01
+
+
+def time_rebuild(mod, u, reps=3):
+    """Median wall time of the 30-round bootstrapped radius + enlargement."""
+    layer = mod.AffineLayer()
+    layer.optimize(u, u)
+    region = mod.MLFriends(u, layer)
+    times, res = [], None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        res = region.compute_enlargement(nbootstraps=NBOOT, rng=np.random.RandomState(2))
+        times.append(time.perf_counter() - t0)
+    return region, float(np.median(times)) * 1e3, res
+
+
 # --------------------------------------------------------------------------------------
 # workload (pure NumPy; identical for both arms)
 # --------------------------------------------------------------------------------------
@@ -252,14 +283,23 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows_per_step": base["rows"], "n_live": N_LIVE, "ndim": NDIM,
-                   "sample": base["sample"]},
+        "config": workload_config(args.gpus, args.batch),
+        "rows_per_step": base["rows"],
         "cpu_baseline": {"value": base["value"], "unit": "points/s", "cores": base["cores"],
                          "kind": base["kind"], "sample": base["sample"]},
         "e2e": {"value": base["value"], "unit": "points/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:   # the region rebuild on one host core, for the rebuild numbers of our arm
+        import ultranest.mlfriends as refmod
+        rebuild = {}
+        for name, u in (("configs[1] N=4000 d=20", make_live()), ("configs[2] eggbox-like N=2000 d=10", multimodal_live())):
+            _, ms, res = time_rebuild(refmod, u, reps=1)
+            rebuild[name] = {"rebuild_ms": ms, "r2": float(res[0]), "f": float(res[1]), "cores": 1}
+        line["rebuild"] = rebuild
+    except Exception as exc:  # noqa: BLE001
+        line["rebuild"] = {"unavailable": str(exc)}
     print(json.dumps(line))
     return 0
 
@@ -431,6 +471,30 @@ def run_ours(args):
     clk = clocks.stop()
     e2e_ok = bool((np_mask.view(np.uint8) == mask_dev.cpu().numpy()).all()) if world == 1 else True
 
+    # ---- (4) region rebuild: 30 bootstrap rounds, un-sharded and (N > 1) sharded over the ranks
+    # with ONE NCCL allreduce(MAX) (integrator.py:388-404); device-timed collective, max over ranks
+    from ultranest_b200 import distributed as D
+    rebuild = {}
+    for name, ulive in (("configs[1] N=4000 d=20", u), ("configs[2] eggbox-like N=2000 d=10", multimodal_live())):
+        reg_r, ms_1, res_1 = time_rebuild(ours, ulive)
+        rec = {"rebuild_ms_1rank": ms_1, "r2": float(res_1[0]), "f": float(res_1[1])}
+        if dist is not None:
+            D.enable()
+            try:
+                times, colls = [], []
+                for _ in range(4):
+                    barrier()
+                    t0 = time.perf_counter()
+                    res_s = reg_r.compute_enlargement(nbootstraps=NBOOT, rng=np.random.RandomState(2))
+                    times.append(max_over_ranks(1e3 * (time.perf_counter() - t0)))
+                    colls.append(max_over_ranks(D.last_timings.get("collective_us", 0.0)))
+                rec.update({"rebuild_ms_sharded": float(np.median(times[1:])),
+                            "collective_us": float(np.median(colls[1:])),
+                            "identical_to_1rank": bool(res_s == res_1), "ranks": world})
+            finally:
+                D.disable()
+        rebuild[name] = rec
+
     if dist is not None:
         dist.barrier()
     if rank != 0:
@@ -487,12 +551,10 @@ def run_ours(args):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "rows_per_step_per_gpu": M, "n_live": N_LIVE, "ndim": NDIM,
-                   "l2_policy": "inputs larger than L2 (%.0f MB of proposals per step)" % (M * NDIM * 8 / 1e6),
-                   "parallelism": "proposal rows sharded over %d GPU(s), no data-path collective" % world,
-                   "accept_fraction": accepted / float(M), "region_rebuild_s": rebuild_s,
-                   "maxradiussq": region.maxradiussq, "enlarge": region.enlarge},
+        "config": workload_config(world, M),
+        "details": {"accept_fraction": accepted / float(M), "region_rebuild_s": rebuild_s,
+                    "maxradiussq": region.maxradiussq, "enlarge": region.enlarge},
+        "rebuild": rebuild,
         "e2e": {"value": world * M * K / (e2e_ms * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms / K, "matches_device_path": e2e_ok,

@@ -46,6 +46,15 @@ extern "C" {
 #define UNB_OPT_FILTER_FP32 3    /* 1 (default): the membership kernel pre-filters pairs in
                                     fp32 (decisions stay exact fp64); 0: fp64 filter only   */
 
+#define UNB_OPT_SURE_LEVEL 4     /* 1 (default): the fp32 membership filter retires a proposal on a
+                                    CERTAIN neighbour (filter value above the whole error budget)
+                                    without an exact evaluation; 0: every flagged pair is decided
+                                    in exact fp64 (A/B switch of the parity tests)            */
+#define UNB_OPT_COOP_MAX 5       /* survivors per block at which the membership kernel's drain turns
+                                    cooperative (0 disables; default 24)                       */
+#define UNB_OPT_BLOCK_KERNEL 6   /* 1: always the block-synchronous membership kernel, also for
+                                    small launches (default 0: warp-independent kernel there)  */
+
 /* unb_ctx_get_stat keys */
 #define UNB_STAT_KERNEL_LAUNCHES 1   /* kernels launched by this ctx since creation       */
 #define UNB_STAT_RECHECKS 2          /* filtered-scan pairs that went to the exact path
@@ -80,6 +89,9 @@ int unb_ctx_synchronize(unb_ctx *ctx);
  * bench.py reports next to the HBM one */
 int unb_fp64_peak(unb_ctx *ctx, double *dfma_per_s);
 int unb_fp32_peak(unb_ctx *ctx, double *ffma_per_s);
+/* the same probe by instruction form: 0 scalar FFMA, 1 packed FFMA2 (fma.rn.f32x2, register
+ * pairs), 2 FFMA2 with a scalar (broadcast) multiplicand -- the form of the membership filter */
+int unb_fp32_peak_form(unb_ctx *ctx, int form, double *lane_fma_per_s);
 
 /* --------------------------------------------- stateless scans (host buffers) */
 
@@ -196,6 +208,22 @@ int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const double *u, s
                          size_t ndim, const uint8_t *selected, size_t nrounds,
                          size_t round_lo, size_t round_hi, const double *ctrs,
                          const double *invcovs, double *maxd_out, double *f_out);
+
+/* The same rounds, folded ON THE DEVICE into the buffer one allreduce(MAX) ships -- the collective
+ * site of _update_region_bootstrap (integrator.py:388-404, comm.gather + np.max + comm.bcast there):
+ *   out5_dev : DEVICE pointer to 5 doubles (e.g. a torch tensor handed to torch.distributed):
+ *              [max_r maxd_r (each float32-rounded), max_r f_r, failed, tag, -tag];
+ *   failed   : 1 if host_failed != 0 (the caller's d x d algebra failed on this rank) or a round has
+ *              f <= 0 / non-finite (mlfriends.pyx:1063-1065); NaN under MAX is undefined in NCCL, so
+ *              failure travels as its own flag (the reference ships NaN, integrator.py:391-393);
+ *   tag      : any value that is equal on all ranks iff they hold the same selection masks (a
+ *              checksum); after the MAX, out[3] == -out[4] proves it.
+ * Only enqueues work on `stream` (NULL: the ctx's own stream); nothing is copied back. */
+int unb_region_bootstrap_fold_dev(unb_ctx *ctx, const double *unormed, const double *u, size_t n,
+                                  size_t ndim, const uint8_t *selected, size_t nrounds,
+                                  size_t round_lo, size_t round_hi, const double *ctrs,
+                                  const double *invcovs, int host_failed, double tag,
+                                  double *out5_dev, void *stream);
 
 /* ---------------------------------------------- vectorised likelihood batch call */
 

@@ -30,6 +30,11 @@ def test_reference_arm_json_line():
     assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0
     assert rec["e2e"]["value"] == rec["value"]
     assert "N_live=4000" in rec["metric"] and rec["config"]["n_live"] == 4000 and rec["config"]["ndim"] == 20
+    # both arms print the SAME config object (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert rec["config"] == bench.workload_config(1, 1 << 20)
+    assert "workload" in rec["config"] and "l2_policy" in rec["config"]
 
 
 def test_bench_help_runs_without_a_gpu():

@@ -1,6 +1,8 @@
-"""world_size=2 gloo tests (CPU) of the multi-GPU host logic: mask broadcast, round slicing, the
-single allreduce(MAX) with its failure flag, row all-gather.  The per-rank round evaluation is
-injected from the oracle, so no GPU is needed; the result must equal the single-process oracle."""
+"""world_size=2 gloo tests (CPU) of the multi-GPU host logic: round slicing, the single
+allreduce(MAX) with its failure flag and mask tag, the optional mask broadcast, exception safety
+(no rank may be left waiting in the collective), row all-gather.  The per-rank round evaluation is
+injected from the oracle, so no GPU is needed; the result must equal the single-process oracle.
+The CUDA path under NCCL is covered by tests/test_gpu_distributed_nccl.py."""
 import os
 import socket
 
@@ -39,6 +41,12 @@ def _failing_rounds(u, unormed, selected, lo, hi, minvol):
     return maxd, f, active, None
 
 
+def _raising_rounds(u, unormed, selected, lo, hi, minvol):
+    if lo > 0:   # an unexpected error (not a numerical failure) on the second rank only
+        raise MemoryError("simulated device allocation failure")
+    return _oracle_rounds(u, unormed, selected, lo, hi, minvol)
+
+
 def _worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -58,13 +66,35 @@ def _worker(rank, world, port, out):
         srng = np.random.RandomState(10 + rank)
         for r in range(7):
             sel[r, srng.randint(300, size=300)] = True
-        r2, f = D.reduce_enlargement(u, unormed, sel, compute_rounds=_oracle_rounds)
+        r2, f = D.reduce_enlargement(u, unormed, sel, compute_rounds=_oracle_rounds, masks="broadcast")
         out.put(("enl", rank, r2, f))
         try:
-            D.reduce_enlargement(u, unormed, sel, compute_rounds=_failing_rounds)
+            D.reduce_enlargement(u, unormed, sel, compute_rounds=_failing_rounds, masks="broadcast")
             out.put(("fail", rank, "no error"))
         except np.linalg.LinAlgError:
             out.put(("fail", rank, "raised"))
+        # replicated masks (the default): different masks are detected by the tag pair that rides
+        # in the same reduction ...
+        try:
+            D.reduce_enlargement(u, unormed, sel, compute_rounds=_oracle_rounds)
+            out.put(("tag", rank, "no error"))
+        except RuntimeError:
+            out.put(("tag", rank, "raised"))
+        # ... identical masks give the single-process result with ONE collective
+        sel0 = np.zeros((7, 300), dtype=bool)
+        srng0 = np.random.RandomState(10)
+        for r in range(7):
+            sel0[r, srng0.randint(300, size=300)] = True
+        r2, f = D.reduce_enlargement(u, unormed, sel0, compute_rounds=_oracle_rounds)
+        out.put(("enl", rank, r2, f))
+        # an exception on one rank must not leave the other waiting in the collective
+        try:
+            D.reduce_enlargement(u, unormed, sel0, compute_rounds=_raising_rounds)
+            out.put(("exc", rank, "no error"))
+        except MemoryError:
+            out.put(("exc", rank, "MemoryError"))
+        except np.linalg.LinAlgError:
+            out.put(("exc", rank, "LinAlgError"))
         rows = np.arange(11 * 3, dtype=np.float64).reshape(11, 3)
         lo, hi = D.shard_bounds(11, world, rank)
         got = D.allgather_rows(rows[lo:hi], 11)
@@ -96,7 +126,7 @@ def test_two_rank_bootstrap_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [out.get(timeout=100) for _ in range(3 * world)]
+    results = [out.get(timeout=100) for _ in range(6 * world)]
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
@@ -113,6 +143,8 @@ def test_two_rank_bootstrap_matches_single_process():
     maxd, f, active, _ = _oracle_rounds(u, unormed, sel, 0, 7, 0.)
     want = (maxd.max(), f.max())
     enl = [r for r in results if r[0] == "enl"]
-    assert len(enl) == 2 and all((r[2], r[3]) == want for r in enl)
+    assert len(enl) == 4 and all((r[2], r[3]) == want for r in enl)
     assert sorted(r[2] for r in results if r[0] == "fail") == ["raised", "raised"]
+    assert sorted(r[2] for r in results if r[0] == "tag") == ["raised", "raised"]
+    assert sorted((r[1], r[2]) for r in results if r[0] == "exc") == [(0, "LinAlgError"), (1, "MemoryError")]
     assert all(r[2] for r in results if r[0] == "gather")

@@ -117,12 +117,12 @@ def eggbox_transform(x):
     return x * 10 * np.pi
 
 
-def run_eggbox(ndim=2, nlive=400, max_ncalls=8000):
+def run_eggbox(ndim=2, nlive=400, max_ncalls=8000, loglike=None):
     """examples/testeggbox.py: many separated modes -> clustering, cluster-centred layers,
     id re-use across rebuilds, a transformed-space wrapping ellipsoid (tregion)."""
     from ultranest import ReactiveNestedSampler
     np.random.seed(3)
-    sampler = ReactiveNestedSampler(["a", "b", "c", "d"][:ndim], eggbox_loglike,
+    sampler = ReactiveNestedSampler(["a", "b", "c", "d"][:ndim], loglike or eggbox_loglike,
                                     transform=eggbox_transform, log_dir=None, vectorized=True)
     res = sampler.run(min_num_live_points=nlive, max_ncalls=max_ncalls, viz_callback=False,
                       show_status=False)
@@ -140,6 +140,22 @@ def test_eggbox_run_is_identical(swapped_modules):
     got = run_eggbox()
     assert got["region"] == "ultranest_b200.mlfriends"
     assert got["tregion"] in (None, "ultranest_b200.mlfriends")
+    for key in ("niter", "ncall", "ncall_region", "nclusters"):
+        assert got[key] == want[key], key
+    assert abs(got["logz"] - want["logz"]) <= 1e-10 * abs(want["logz"])
+
+
+def test_eggbox_run_with_device_likelihood_logz(swapped_modules):
+    """The same seeded eggbox run with the DEVICE likelihood batch call (`EggboxLogLike`: CUDA
+    cos/pow, <= 2 ulp from libm, so not bit-identical to NumPy): logZ must stay within the 1e-10
+    relative bar of BASELINE.json, and -- ulp-level likelihood noise never reorders the dead
+    points here -- the run must be the same run (niter, ncall, cluster count)."""
+    want = run_eggbox()
+    import ultranest_b200
+    from ultranest_b200.likelihoods import EggboxLogLike
+    ultranest_b200.install(force=True)
+    got = run_eggbox(loglike=EggboxLogLike())
+    assert got["region"] == "ultranest_b200.mlfriends"
     for key in ("niter", "ncall", "ncall_region", "nclusters"):
         assert got[key] == want[key], key
     assert abs(got["logz"] - want["logz"]) <= 1e-10 * abs(want["logz"])

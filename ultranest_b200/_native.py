@@ -22,6 +22,9 @@ UNB_ERR_NUMERIC = -5
 OPT_EXACT_ONLY = 1
 OPT_CHUNK_ROWS = 2
 OPT_FILTER_FP32 = 3
+OPT_SURE_LEVEL = 4
+OPT_COOP_MAX = 5
+OPT_BLOCK_KERNEL = 6
 STAT_KERNEL_LAUNCHES = 1
 STAT_RECHECKS = 2
 STAT_H2D_BYTES = 3
@@ -58,6 +61,7 @@ SIGNATURES = {
     "unb_ctx_synchronize": [],
     "unb_fp64_peak": [_c_dp],
     "unb_fp32_peak": [_c_dp],
+    "unb_fp32_peak_form": [_int, _c_dp],
     "unb_find_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_count_nearby": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
     "unb_has_neighbour": [_c_vp, _sz, _c_vp, _sz, _sz, _dbl, _c_vp],
@@ -84,6 +88,8 @@ SIGNATURES = {
     "unb_region_find_nearby_dev": [_c_vp, _sz, _c_vp, _c_vp, _c_vp],
     "unb_region_bootstrap": [_c_vp, _c_vp, _sz, _sz, _c_vp, _sz, _sz, _sz, _c_vp, _c_vp,
                              _c_vp, _c_vp],
+    "unb_region_bootstrap_fold_dev": [_c_vp, _c_vp, _sz, _sz, _c_vp, _sz, _sz, _sz, _c_vp, _c_vp,
+                                      _int, _dbl, _c_vp, _c_vp],
     "unb_loglike_gauss": [_c_vp, _sz, _sz, _c_vp, _c_vp, _dbl, _dbl],
     "unb_loglike_rosenbrock": [_c_vp, _sz, _sz, _c_vp],
     "unb_loglike_eggbox": [_c_vp, _sz, _sz, _c_vp],
@@ -229,6 +235,13 @@ class Engine(object):
         """Measured fp32 FMA rate of this device (lane-FMAs per second)."""
         v = _dbl(0.0)
         self.call("unb_fp32_peak", ctypes.byref(v))
+        return float(v.value)
+
+    def fp32_peak_form(self, form):
+        """The fp32 probe by instruction form: 0 scalar FFMA, 1 packed FFMA2, 2 FFMA2 with a
+        scalar multiplicand (lane-FMAs per second)."""
+        v = _dbl(0.0)
+        self.call("unb_fp32_peak_form", int(form), ctypes.byref(v))
         return float(v.value)
 
     def fp64_peak(self):
@@ -425,6 +438,24 @@ class Engine(object):
                   _ptr(ctrs) if want_f else None, _ptr(invcovs) if want_f else None,
                   _ptr(maxd), _ptr(f))
         return maxd, f
+
+    def region_bootstrap_fold_dev(self, unormed, selected, u, ctrs, invcovs, round_lo, round_hi,
+                                  host_failed, tag, out_ptr, stream=None):
+        """Rounds ``[round_lo, round_hi)`` folded on the device into the 5-double buffer at the
+        DEVICE address ``out_ptr`` (``[r2, f, failed, tag, -tag]``); only enqueues work."""
+        t = as_f64(unormed, 2)
+        u = as_f64(u, 2)
+        n, d = t.shape
+        sel = np.ascontiguousarray(selected, dtype=np.uint8)
+        nrounds = sel.shape[0]
+        ctrs = as_f64(ctrs, 2)
+        invcovs = as_f64(invcovs, 3)
+        if (sel.ndim != 2 or sel.shape[1] != n or u.shape != (n, d) or ctrs.shape != (nrounds, d)
+                or invcovs.shape != (nrounds, d, d)):
+            raise ValueError("bootstrap shapes mismatch")
+        self.call("unb_region_bootstrap_fold_dev", _ptr(t), _ptr(u), n, d, _ptr(sel), nrounds,
+                  int(round_lo), int(round_hi), _ptr(ctrs), _ptr(invcovs), 1 if host_failed else 0,
+                  float(tag), int(out_ptr), stream)
 
     # -- likelihoods -----------------------------------------------------------------------
     def loglike_gauss(self, theta, centers, sigma, norm_const):

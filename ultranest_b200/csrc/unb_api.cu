@@ -177,11 +177,10 @@ ScanArgs scan_args_for(const LiveTiles &L)
 }
 
 // largest squared norm of the live block for the certain-neighbour level of the fp32 membership
-// filter (unb_scan.cu, tile_filter32); UNB_ANY32_NOSURE=1 switches the shortcut off (A/B, tests)
-double sure_namax(const LiveTiles &L)
+// filter (unb_scan.cu, tile_filter32); UNB_OPT_SURE_LEVEL = 0 switches the shortcut off (tests)
+double sure_namax(const unb_ctx *ctx, const LiveTiles &L)
 {
-    static const bool off = getenv("UNB_ANY32_NOSURE") != nullptr;
-    return off ? (double)INFINITY : L.namax_host;
+    return ctx->sure_level ? L.namax_host : (double)INFINITY;
 }
 
 // threshold-mode h row + (when safe and enabled) the fp32 image used by the membership kernel
@@ -194,7 +193,7 @@ int prepare_threshold(unb_ctx *ctx, LiveTiles &L, double r2, cudaStream_t s, Sca
     if (a && ok32) {
         a->tiles32 = (const float *)L.tiles32.p;
         a->kappa32 = unb_kappa32(L.d);
-        a->namax32 = sure_namax(L);
+        a->namax32 = sure_namax(ctx, L);
     }
     return UNB_OK;
 }
@@ -335,6 +334,9 @@ extern "C" int unb_ctx_set_option(unb_ctx *ctx, int option, int64_t value)
     case UNB_OPT_EXACT_ONLY: ctx->exact_only = value ? 1 : 0; return UNB_OK;
     case UNB_OPT_CHUNK_ROWS: ctx->chunk_rows = value > 0 ? value : 0; return UNB_OK;
     case UNB_OPT_FILTER_FP32: ctx->filter_fp32 = value ? 1 : 0; return UNB_OK;
+    case UNB_OPT_SURE_LEVEL: ctx->sure_level = value ? 1 : 0; return UNB_OK;
+    case UNB_OPT_COOP_MAX: ctx->coop_max = value < 0 ? 0 : (int)(value > 1 << 20 ? 1 << 20 : value); return UNB_OK;
+    case UNB_OPT_BLOCK_KERNEL: ctx->block_kernel = value ? 1 : 0; return UNB_OK;
     default: return unb_fail(ctx, UNB_ERR_ARG, "unknown option %d", option);
     }
 }
@@ -389,29 +391,49 @@ extern "C" int unb_fp64_peak(unb_ctx *ctx, double *dfma_per_s)
     return UNB_OK;
 }
 
-extern "C" int unb_fp32_peak(unb_ctx *ctx, double *ffma_per_s)
+extern "C" int unb_fp32_peak_form(unb_ctx *ctx, int form, double *lane_fma_per_s)
 {
     UNB_TRY(check_ctx(ctx));
-    if (!ffma_per_s) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (!lane_fma_per_s) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (form < 0 || form > 2) return unb_fail(ctx, UNB_ERR_ARG, "unknown instruction form %d", form);
     cudaStream_t s = S0(ctx);
     UNB_TRY(unb_reserve(ctx, ctx->aux0, 64));
-    const int blocks = ctx->sm_count * 8, iters = 40000;
+    const int blocks = ctx->sm_count * 8, iters = form == 0 ? 40000 : 20000;
+    const double per_iter = form == 0 ? 8.0 : 16.0;   // lane-FMAs per thread and iteration
     cudaEvent_t e0, e1;
     UNB_CUDA(ctx, cudaEventCreate(&e0));
     UNB_CUDA(ctx, cudaEventCreate(&e1));
     double best = 0.0;
     for (int rep = 0; rep < 4; rep++) {
         UNB_CUDA(ctx, cudaEventRecord(e0, s));
-        UNB_TRY(unb_launch_fp32_peak(ctx, (float *)ctx->aux0.p, blocks, iters, s));
+        UNB_TRY(unb_launch_fp32_peak(ctx, (float *)ctx->aux0.p, form == 2 ? -blocks : blocks,
+                                     form == 0 ? iters : -iters, s));
         UNB_CUDA(ctx, cudaEventRecord(e1, s));
         UNB_CUDA(ctx, cudaEventSynchronize(e1));
         float ms = 0.f;
         UNB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
-        const double rate = (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3);
+        const double rate = (double)blocks * 256.0 * per_iter * iters / (ms * 1e-3);
         if (rep > 0 && rate > best) best = rate;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    *lane_fma_per_s = best;
+    return UNB_OK;
+}
+
+// the fp32 roofline denominator: the best rate over the instruction forms (the membership filter
+// issues FFMA2 with a scalar multiplicand; a device where the packed form is no faster reports
+// the scalar rate)
+extern "C" int unb_fp32_peak(unb_ctx *ctx, double *ffma_per_s)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!ffma_per_s) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    double best = 0.0;
+    for (int form = 0; form < 3; form++) {
+        double r = 0.0;
+        UNB_TRY(unb_fp32_peak_form(ctx, form, &r));
+        if (r > best) best = r;
+    }
     *ffma_per_s = best;
     return UNB_OK;
 }
@@ -874,7 +896,7 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
         if (have32) {
             a.tiles32 = (const float *)R.live.tiles32.p;   // prepared by the caller (set_h stage)
             a.kappa32 = unb_kappa32(R.live.d);
-            a.namax32 = sure_namax(R.live);
+            a.namax32 = sure_namax(ctx, R.live);
         }
         UNB_TRY(unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s));
     } else {
@@ -1331,35 +1353,35 @@ extern "C" int unb_region_count_nearby(unb_ctx *ctx, const double *tpts, size_t 
 // ---------------------------------------------------------------------------------------
 // bootstrap
 // ---------------------------------------------------------------------------------------
-extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const double *u, size_t n,
-                                    size_t ndim, const uint8_t *selected, size_t nrounds,
-                                    size_t round_lo, size_t round_hi, const double *ctrs,
-                                    const double *invcovs, double *maxd_out, double *f_out)
-{
-    UNB_TRY(check_ctx(ctx));
-    UNB_TRY(check_dims(ctx, n, ndim));
-    const bool want_d = unormed && maxd_out;
-    const bool want_f = u && ctrs && invcovs && f_out;
-    if (!selected || n == 0 || (!want_d && !want_f))
-        return unb_fail(ctx, UNB_ERR_ARG, "null pointer / empty live block");
-    if (round_hi > nrounds) round_hi = nrounds;
-    if (round_lo >= round_hi) return UNB_OK;
-    cudaStream_t s = S0(ctx);
-    const size_t d = ndim;
+namespace {
 
+// what bootstrap_enqueue leaves behind: per-active-round results on the device
+struct BootRounds {
+    std::vector<int> round_of;         // active slot -> round
+    unsigned long long *dMax = nullptr;   // [R] bits of the round's max-min squared distance
+    unsigned long long *dF = nullptr;     // [R] total-order keys of the round's einsum maximum
+    bool want_d = false, want_f = false;
+};
+
+// Enqueues the device half of rounds [round_lo, round_hi) on stream s: index lists of the active
+// rounds (host), gather of the per-round tiles, the max-min scan of all rounds in one launch and
+// the per-round einsum maxima.  Nothing is read back here.
+int bootstrap_enqueue(unb_ctx *ctx, const double *unormed, const double *u, size_t n, size_t ndim,
+                      const uint8_t *selected, size_t round_lo, size_t round_hi, const double *ctrs,
+                      const double *invcovs, bool want_d, bool want_f, cudaStream_t s, BootRounds *B)
+{
+    const size_t d = ndim;
+    B->want_d = want_d;
+    B->want_f = want_f;
     // host: index lists of the active rounds (selection masks come from the host RNG in the
     // reference's order; rounds with all/none selected are skipped like mlfriends.pyx:1048-1049)
-    std::vector<int> round_of;          // active slot -> round
+    std::vector<int> &round_of = B->round_of;
     std::vector<int> idxA, idxB, offA, offB, nA, nB;
     for (size_t r = round_lo; r < round_hi; r++) {
         const uint8_t *sel = selected + r * n;
         size_t ca = 0;
         for (size_t i = 0; i < n; i++) ca += sel[i] ? 1 : 0;
-        if (ca == 0 || ca == n) {
-            if (want_d) maxd_out[r] = 0.0;
-            if (want_f) f_out[r] = 0.0;
-            continue;
-        }
+        if (ca == 0 || ca == n) continue;
         round_of.push_back((int)r);
         offA.push_back((int)idxA.size());
         offB.push_back((int)idxB.size());
@@ -1394,6 +1416,8 @@ extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const d
     UNB_CUDA(ctx, cudaMemsetAsync(ctx->boot_out.p, 0, 2 * (size_t)R * sizeof(unsigned long long), s));
     unsigned long long *dMax = (unsigned long long *)ctx->boot_out.p;
     unsigned long long *dF = dMax + R;
+    B->dMax = dMax;
+    B->dF = dF;
 
     int maxB = 0;
     for (int r = 0; r < R; r++) maxB = std::max(maxB, nB[r]);
@@ -1439,6 +1463,8 @@ extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const d
         UNB_TRY(unb_reserve(ctx, ctx->boot_u, n * d * sizeof(double)));
         UNB_TRY(h2d(ctx, ctx->boot_u.p, u, n * d * sizeof(double), s));
         UNB_TRY(unb_reserve_pinned(ctx, ctx->pin_small, (size_t)R * (d + d * d) * sizeof(double)));
+        // the pinned block may still be read by an earlier call's copy on another stream
+        UNB_CUDA(ctx, cudaStreamSynchronize(s));
         double *hc = (double *)ctx->pin_small.p;
         double *ha = hc + (size_t)R * d;
         for (int r = 0; r < R; r++) {
@@ -1452,6 +1478,65 @@ extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const d
         UNB_TRY(unb_launch_enlargement_f(ctx, (const double *)ctx->boot_u.p, (int)d, dB, dOffB, dNB,
                                          maxB, dC, dAinv, R, dF, s));
     }
+    return UNB_OK;
+}
+
+// Folds the per-round device results into the 5 doubles one allreduce(MAX) ships
+// (integrator.py:395-404): [max radius^2 (each round rounded to float32 like the reference's C
+// `float` return), max enlargement, failure flag (a round with f <= 0 or non-finite,
+// mlfriends.pyx:1063-1065), tag, -tag].  The tag pair lets the ranks verify after the MAX that
+// they all worked on the same selection masks (max(tag) == -max(-tag) iff all tags agree).
+__global__ void k_boot_fold(const unsigned long long *__restrict__ dMax,
+                            const unsigned long long *__restrict__ dF, int R, int want_d, int want_f,
+                            double failed_in, double tag, double *__restrict__ out)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double maxd = 0.0, maxf = 0.0, failed = failed_in;
+    for (int r = 0; r < R; r++) {
+        if (want_d) {
+            const double v = (double)(float)__longlong_as_double((long long)dMax[r]);
+            maxd = v > maxd ? v : maxd;
+        }
+        if (want_f) {
+            const unsigned long long key = dF[r];
+            const unsigned long long bits = (key >> 63) ? (key & 0x7fffffffffffffffULL) : ~key;
+            const double f = __longlong_as_double((long long)bits);
+            if (!(f > 0.0) || isinf(f) || isnan(f)) failed = 1.0;
+            else maxf = f > maxf ? f : maxf;
+        }
+    }
+    out[0] = maxd;
+    out[1] = maxf;
+    out[2] = failed;
+    out[3] = tag;
+    out[4] = -tag;
+}
+
+}  // namespace
+
+extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const double *u, size_t n,
+                                    size_t ndim, const uint8_t *selected, size_t nrounds,
+                                    size_t round_lo, size_t round_hi, const double *ctrs,
+                                    const double *invcovs, double *maxd_out, double *f_out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, n, ndim));
+    const bool want_d = unormed && maxd_out;
+    const bool want_f = u && ctrs && invcovs && f_out;
+    if (!selected || n == 0 || (!want_d && !want_f))
+        return unb_fail(ctx, UNB_ERR_ARG, "null pointer / empty live block");
+    if (round_hi > nrounds) round_hi = nrounds;
+    if (round_lo >= round_hi) return UNB_OK;
+    cudaStream_t s = S0(ctx);
+    for (size_t r = round_lo; r < round_hi; r++) {   // inactive rounds report 0
+        if (want_d) maxd_out[r] = 0.0;
+        if (want_f) f_out[r] = 0.0;
+    }
+    BootRounds B;
+    UNB_TRY(bootstrap_enqueue(ctx, unormed, u, n, ndim, selected, round_lo, round_hi, ctrs, invcovs,
+                              want_d, want_f, s, &B));
+    const int R = (int)B.round_of.size();
+    if (R == 0) return UNB_OK;
     std::vector<unsigned long long> out(2 * (size_t)R);
     UNB_TRY(d2h(ctx, out.data(), ctx->boot_out.p, 2 * (size_t)R * sizeof(unsigned long long), s));
     UNB_TRY(stat_fetch(ctx, s));
@@ -1459,16 +1544,42 @@ extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const d
         if (want_d) {
             double maxd;
             memcpy(&maxd, &out[r], sizeof(double));
-            maxd_out[round_of[r]] = (double)(float)maxd;   // C `float` return (mlfriends.pyx:188)
+            maxd_out[B.round_of[r]] = (double)(float)maxd;   // C `float` return (mlfriends.pyx:188)
         }
         if (want_f) {
             unsigned long long key = out[R + r];
             unsigned long long bits = (key >> 63) ? (key & 0x7fffffffffffffffULL) : ~key;
             double f;
             memcpy(&f, &bits, sizeof(double));
-            f_out[round_of[r]] = f;
+            f_out[B.round_of[r]] = f;
         }
     }
+    return UNB_OK;
+}
+
+extern "C" int unb_region_bootstrap_fold_dev(unb_ctx *ctx, const double *unormed, const double *u,
+                                             size_t n, size_t ndim, const uint8_t *selected,
+                                             size_t nrounds, size_t round_lo, size_t round_hi,
+                                             const double *ctrs, const double *invcovs,
+                                             int host_failed, double tag, double *out5_dev,
+                                             void *stream)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, n, ndim));
+    const bool want_d = unormed != nullptr;
+    const bool want_f = u && ctrs && invcovs;
+    if (!selected || !out5_dev || n == 0 || (!want_d && !want_f))
+        return unb_fail(ctx, UNB_ERR_ARG, "null pointer / empty live block");
+    if (round_hi > nrounds) round_hi = nrounds;
+    cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
+    BootRounds B;
+    if (round_lo < round_hi)
+        UNB_TRY(bootstrap_enqueue(ctx, unormed, u, n, ndim, selected, round_lo, round_hi, ctrs,
+                                  invcovs, want_d, want_f, s, &B));
+    k_boot_fold<<<1, 32, 0, s>>>(B.dMax, B.dF, (int)B.round_of.size(), want_d ? 1 : 0,
+                                 want_f ? 1 : 0, host_failed ? 1.0 : 0.0, tag, out5_dev);
+    ctx->launches++;
+    UNB_CUDA(ctx, cudaGetLastError());
     return UNB_OK;
 }
 

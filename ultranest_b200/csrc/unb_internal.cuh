@@ -169,6 +169,9 @@ struct unb_ctx {
     long long last_tile_visits = 0;
     int exact_only = 0;
     int filter_fp32 = 1;
+    int sure_level = 1;      // UNB_OPT_SURE_LEVEL
+    int coop_max = -1;       // UNB_OPT_COOP_MAX (-1: the kernel's default)
+    int block_kernel = 0;    // UNB_OPT_BLOCK_KERNEL
     long long chunk_rows = 0;
 
     Lane lane[2];
@@ -349,6 +352,19 @@ __device__ __forceinline__ double sq_step(double acc, double a, double b)
 {
     double diff = __dsub_rn(a, b);
     return __dadd_rn(acc, __dmul_rn(diff, diff));
+}
+
+// Packed single-precision FMA (Blackwell FFMA2): d.x = a.x*b.x + c.x, d.y = a.y*b.y + c.y, each
+// lane rounded to nearest once, i.e. exactly two fmaf().  One issue slot for two FMAs; a scalar
+// broadcast make_float2(s, s) folds into the instruction's .F32 operand form (no extra MOV).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra, rb, rc, rd;
+    ra = *reinterpret_cast<unsigned long long *>(&a);
+    rb = *reinterpret_cast<unsigned long long *>(&b);
+    rc = *reinterpret_cast<unsigned long long *>(&c);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
 }
 
 #endif  // __CUDACC__

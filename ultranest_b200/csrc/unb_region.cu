@@ -740,10 +740,37 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float 
     if (r == 12345.678f) out[0] = r;
 }
 
+// packed form: 8 independent FFMA2 chains (16 lane-FMAs per iteration and thread)
+template <bool BCAST>
+__global__ void __launch_bounds__(256) k_fp32x2_peak(float *out, int iters, float seed)
+{
+    float2 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = make_float2(seed + threadIdx.x + i, seed - i);
+    const float ms = 1.0000001f + 1e-7f * (float)(threadIdx.x & 1);
+    const float2 m = BCAST ? make_float2(ms, ms) : make_float2(ms, 1.0000002f);
+    const float2 c = make_float2(1e-7f, 2e-7f);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = BCAST ? ffma2(m, a[i], c) : ffma2(a[i], m, c);
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r += a[i].x + a[i].y;
+    if (r == 12345.678f) out[0] = r;
+}
+
 }  // namespace
 
 int unb_launch_fp32_peak(unb_ctx *ctx, float *scratch, int blocks, int iters, cudaStream_t s)
 {
+    if (iters < 0) {   // packed forms: -iters iterations; blocks < 0 selects the broadcast form
+        if (blocks < 0) k_fp32x2_peak<true><<<-blocks, 256, 0, s>>>(scratch, -iters, 1.0f);
+        else k_fp32x2_peak<false><<<blocks, 256, 0, s>>>(scratch, -iters, 1.0f);
+        ctx->launches++;
+        UNB_CUDA(ctx, cudaGetLastError());
+        return UNB_OK;
+    }
     k_fp32_peak<<<blocks, 256, 0, s>>>(scratch, iters, 1.0f);
     ctx->launches++;
     UNB_CUDA(ctx, cudaGetLastError());

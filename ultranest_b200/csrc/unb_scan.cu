@@ -696,12 +696,16 @@ __device__ __forceinline__ void tile_filter32(const float (&a)[TM][DR], float (&
 #pragma unroll 1
     for (int g = 0; g < REG_TILE_N / TN; g++) {
         const float *Tg = T + g * TN;
-        float acc[TMA][TN];
+        // two packed FMAs (FFMA2) per slot and k: live points (0,1) and (2,3) of the group ride
+        // in 64-bit register pairs, the proposal coordinate is the instruction's scalar operand.
+        // Each half is one fmaf(): the filter's arithmetic (and its error budget) is unchanged.
+        float2 acc01[TMA], acc23[TMA];
         {
             const float4 h = *reinterpret_cast<const float4 *>(Tg + DR * REG_TILE_N);
 #pragma unroll
             for (int m = 0; m < TMA; m++) {
-                acc[m][0] = h.x; acc[m][1] = h.y; acc[m][2] = h.z; acc[m][3] = h.w;
+                acc01[m] = make_float2(h.x, h.y);
+                acc23[m] = make_float2(h.z, h.w);
             }
         }
 #pragma unroll
@@ -709,11 +713,16 @@ __device__ __forceinline__ void tile_filter32(const float (&a)[TM][DR], float (&
             const float4 b = *reinterpret_cast<const float4 *>(Tg + k * REG_TILE_N);
 #pragma unroll
             for (int m = 0; m < TMA; m++) {
-                acc[m][0] = fmaf(a[m][k], b.x, acc[m][0]);
-                acc[m][1] = fmaf(a[m][k], b.y, acc[m][1]);
-                acc[m][2] = fmaf(a[m][k], b.z, acc[m][2]);
-                acc[m][3] = fmaf(a[m][k], b.w, acc[m][3]);
+                const float2 am = make_float2(a[m][k], a[m][k]);
+                acc01[m] = ffma2(am, make_float2(b.x, b.y), acc01[m]);
+                acc23[m] = ffma2(am, make_float2(b.z, b.w), acc23[m]);
             }
+        }
+        float acc[TMA][TN];
+#pragma unroll
+        for (int m = 0; m < TMA; m++) {
+            acc[m][0] = acc01[m].x; acc[m][1] = acc01[m].y;
+            acc[m][2] = acc23[m].x; acc[m][3] = acc23[m].y;
         }
 #pragma unroll
         for (int m = 0; m < TMA; m++) {
@@ -979,19 +988,21 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                     }
                     if (!any_act) continue;
                     const float2 h = *reinterpret_cast<const float2 *>(T2 + DR * REG_TILE_N + 2 * lane);
-                    float acc0[COOP_G], acc1[COOP_G];
+                    float2 acc2[COOP_G];
 #pragma unroll
-                    for (int g = 0; g < COOP_G; g++) { acc0[g] = h.x; acc1[g] = h.y; }
+                    for (int g = 0; g < COOP_G; g++) acc2[g] = h;
 #pragma unroll
                     for (int k = 0; k < DR; k++) {
                         const float2 bb = *reinterpret_cast<const float2 *>(T2 + k * REG_TILE_N + 2 * lane);
 #pragma unroll
                         for (int g = 0; g < COOP_G; g++) {
                             const float c = __int_as_float((int)stage[k * ANY_STAGE_SLOTS + jg[g]]);
-                            acc0[g] = fmaf(c, bb.x, acc0[g]);
-                            acc1[g] = fmaf(c, bb.y, acc1[g]);
+                            acc2[g] = ffma2(make_float2(c, c), bb, acc2[g]);
                         }
                     }
+                    float acc0[COOP_G], acc1[COOP_G];
+#pragma unroll
+                    for (int g = 0; g < COOP_G; g++) { acc0[g] = acc2[g].x; acc1[g] = acc2[g].y; }
 #pragma unroll
                     for (int g = 0; g < COOP_G; g++) {
                         if (rg[g] < 0) continue;
@@ -1665,7 +1676,7 @@ int launch_any(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
 template <int DR, int TM>
 int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t s)
 {
-    static const bool blocksync = getenv("UNB_ANY32_BLOCKSYNC") != nullptr;   // A/B switch
+    const bool blocksync = ctx->block_kernel != 0;   // UNB_OPT_BLOCK_KERNEL
     long long bx = (a.n_items + SCAN_THREADS * TM - 1) / (SCAN_THREADS * TM);
     // Warp-independent streams win on small launches (latency: no barrier, warps retire alone;
     // measured 0.127 vs 0.150 ms at 4096 proposals, 333 vs 428 us per integrator iteration); the
@@ -1700,11 +1711,8 @@ int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t 
     const long long resident = (long long)per_sm * ctx->sm_count;
     if (bx > resident) bx = resident;
     if (bx < 1) bx = 1;
-    static const int coop_max = []() {
-        const char *e = getenv("UNB_ANY32_COOP");   // experiment switch
-        int v = e ? atoi(e) : ANY_COOP_MAX;
-        return v < 0 ? 0 : (v > ANY_STAGE_SLOTS ? ANY_STAGE_SLOTS : v);
-    }();
+    int coop_max = ctx->coop_max < 0 ? ANY_COOP_MAX : ctx->coop_max;   // UNB_OPT_COOP_MAX
+    if (coop_max > ANY_STAGE_SLOTS) coop_max = ANY_STAGE_SLOTS;
     ScanArgs ac = a;
     ac.coop_max = coop_max;
     k_inside_any32<DR, TM><<<(unsigned)bx, SCAN_THREADS, smem, s>>>(ac, queue_head);

@@ -298,7 +298,9 @@ __global__ void k_step_back(double Lmin, double *__restrict__ allL, long long nw
     while (remaining > 0) {                              // :319-334, this walker's share
         const long long ga = g < 0 ? g + ncols : g;      // NumPy index wrap of allL[i, g]
         const long long gb = g < 0 ? g + max_width : g;  // ... and of below_threshold_parent[., g]
-        if (ga < 0 || gb < 0) break;                     // the reference raises IndexError here
+        // out-of-range generations raise IndexError in the reference; the host mirror validates
+        // them before the launch (stepfuncs.step_back), the kernel never writes out of bounds
+        if (ga < 0 || gb < 0 || ga >= ncols || gb >= max_width) break;
         row[ga] = nan;
         const unsigned long long bit = 1ull << (gb & 63);
         if (bits[gb >> 6] & bit) {

@@ -7,19 +7,25 @@ Where the path shards:
   rank takes a contiguous slice, no data-path collective; :func:`allgather_rows` re-unites masks
   when a caller needs the full vector.
 * **bootstrap rounds** are independent: rank ``r`` evaluates rounds ``[lo_r, hi_r)`` and ONE
-  ``all_reduce(MAX)`` over a 3-double buffer ``[r2, f, failure]`` replaces the reference's
-  pickled ``gather`` + ``bcast`` (``integrator.py:395-404``).  For parity with the
-  single-process oracle the selection masks of ALL rounds come from rank 0's host stream
-  (the reference's MPI mode re-seeds every rank, ``integrator.py:1239-1251``, and is therefore
-  not comparable with its own 1-process run).
+  ``all_reduce(MAX)`` over a 5-double device buffer ``[r2, f, failure, tag, -tag]`` replaces the
+  reference's pickled ``gather`` + ``bcast`` (``integrator.py:395-404``).  The per-round results
+  are folded into that buffer on the device (``unb_region_bootstrap_fold_dev``) and reduced in
+  place by NCCL; the host reads 40 bytes once, after the collective.  For parity with the
+  single-process oracle every rank draws the selection masks of ALL rounds from its own,
+  identically seeded host stream (torchrun replicas of one seeded sampler); the tag pair proves
+  that they agree.  (The reference's MPI mode re-seeds every rank, ``integrator.py:1239-1251``,
+  and is therefore not comparable with its own 1-process run)
 
 Backend: ``nccl`` on GPUs (NVLink 5 / NVSwitch), ``gloo`` in the CPU-only tests.  The payload is
-24 bytes, so the collective is latency-bound; there is nothing to overlap or fuse.
+40 bytes, so the collective is latency-bound; there is nothing to overlap or fuse.
 """
 import numpy as np
 
 _enabled = False
 _group = None
+# {"collective_us": ...} of the most recent reduce_enlargement on this rank (CUDA events around the
+# all_reduce on the current stream; NCCL only) -- read by bench.py and the NCCL tests
+last_timings = {}
 
 
 def _dist():
@@ -111,40 +117,128 @@ def allgather_rows(local, total_rows):
     return np.concatenate(parts, axis=0)
 
 
-def reduce_enlargement(u, unormed, selected, minvol=0., compute_rounds=None):
-    """Sharded ``compute_enlargement``: masks from rank 0, this rank's slice of rounds on its GPU,
-    one ``all_reduce(MAX)`` of ``[r2, f, failed]``.  Returns ``(r2, f)``, identical on all ranks
-    and identical to the single-process result (max is order-independent).
+def _mask_tag(selected):
+    """A checksum of the selection masks that is exact in a float64 (< 2^52): equal on all ranks
+    iff they drew the same rounds.  Rides in the same reduction as ``[tag, -tag]``."""
+    import zlib
+    sel = np.ascontiguousarray(selected, dtype=np.uint8)
+    crc = zlib.crc32(sel.tobytes()) & 0xffffffff
+    return float(crc * 1024 + (sel.shape[0] % 1024))
 
+
+def _host_rounds(u, selected, lo, hi, minvol):
+    """The d x d host algebra of rounds ``[lo, hi)`` (``bounding_ellipsoid`` + ``inv``,
+    mlfriends.pyx:1057-1058).  Returns ``(ctrs, invcovs, stop, failure)``: rounds from ``stop`` on
+    are not evaluated because the algebra of round ``stop`` failed (``failure`` is the exception)."""
+    from .mlfriends import bounding_ellipsoid
+    nrounds = selected.shape[0]
+    ndim = u.shape[1]
+    active = ~(selected.all(axis=1) | ~selected.any(axis=1))
+    ctrs = np.zeros((nrounds, ndim))
+    invcovs = np.zeros((nrounds, ndim, ndim))
+    for r in range(lo, hi):
+        if not active[r]:
+            continue
+        try:
+            ctr, cov = bounding_ellipsoid(u[selected[r], :], minvol=minvol)
+            invcovs[r] = np.linalg.inv(cov)
+            ctrs[r] = ctr
+        except (np.linalg.LinAlgError, FloatingPointError, AssertionError, Warning) as exc:
+            return ctrs, invcovs, r, exc
+    return ctrs, invcovs, hi, None
+
+
+def reduce_enlargement(u, unormed, selected, minvol=0., compute_rounds=None, masks="replicated",
+                       timings=None):
+    """Sharded ``compute_enlargement``: this rank's slice of the rounds on its GPU and ONE
+    ``all_reduce(MAX)`` of ``[r2, f, failed, tag, -tag]`` -- the reference's ``comm.gather`` +
+    ``np.max`` + ``comm.bcast`` (integrator.py:395-404) as a single exchange.  Returns
+    ``(r2, f)``, identical on all ranks and identical to the single-process result (max is
+    order-independent).
+
+    ``masks="replicated"`` (default): every rank drew ``selected`` itself from an identically
+    seeded stream (torchrun replicas of one seeded sampler); the tag pair in the same reduction
+    proves it, a mismatch raises.  ``masks="broadcast"``: rank 0's masks are shipped first (a
+    second collective) -- for callers whose ranks do not share a random stream.
+
+    On NCCL the per-round results never visit the host: the library folds them on the device
+    into the 5-double buffer that the collective reduces in place (``unb_region_bootstrap_fold_dev``).
     ``compute_rounds(u, unormed, selected, lo, hi, minvol) -> (maxd_r, f_r, active, failure)``
-    defaults to the device implementation; the CPU tests inject the oracle here.
+    replaces the device path (the CPU tests inject the oracle here; gloo has no device buffer).
+    Any exception on one rank still reaches the collective (failed flag), so no rank is left
+    waiting; it is re-raised afterwards on the rank that had it, ``LinAlgError`` on the others.
     """
-    if compute_rounds is None:
-        from .mlfriends import _bootstrap_rounds as compute_rounds
+    import torch
+    dist = _dist()
     world, me = world_size(), rank()
-    selected = broadcast_array(np.asarray(selected, dtype=np.uint8)).astype(bool)
+    if masks == "broadcast":
+        selected = broadcast_array(np.asarray(selected, dtype=np.uint8)).astype(bool)
+    elif masks != "replicated":
+        raise ValueError("masks must be 'replicated' or 'broadcast'")
+    selected = np.asarray(selected, dtype=bool)
     nrounds = selected.shape[0]
     lo, hi = shard_bounds(nrounds, world, me)
-    maxd, maxf, failed = 0.0, 0.0, 0.0
+    tag = _mask_tag(selected)
+    dev = _device()
+    on_device = compute_rounds is None and dev.type == "cuda"
+    local_exc = None
     message = None
-    if hi > lo:
-        maxd_r, f_r, active, failure = compute_rounds(u, unormed, selected, lo, hi, minvol)
-        if failure is not None:
-            failed, message = 1.0, str(failure[1])
-        for r in range(lo, hi):
-            if not active[r]:
-                continue
-            if failure is not None and r >= failure[0]:
-                break
-            maxd = max(maxd, maxd_r[r])
-            f = f_r[r]
-            if not np.isfinite(f) or not f > 0:
-                failed, message = 1.0, "Distances are not positive"
-                break
-            maxf = max(maxf, f)
+    buf = None
+    try:
+        if on_device:
+            from .mlfriends import _engine
+            ctrs, invcovs, stop, failure = _host_rounds(u, selected, lo, hi, minvol)
+            if failure is not None:
+                local_exc, message = failure, str(failure)
+            buf = torch.empty(5, dtype=torch.float64, device=dev)
+            # the fold kernel must precede the collective in stream order: torch's current stream
+            # (handle 0 = the legacy default stream, spelled cudaStreamLegacy = 1 for the library,
+            # whose own streams do not synchronise with it)
+            stream = torch.cuda.current_stream(dev).cuda_stream or 1
+            _engine().region_bootstrap_fold_dev(unormed, selected, u, ctrs, invcovs, lo, stop,
+                                                failure is not None, tag, buf.data_ptr(), stream)
+        else:
+            if compute_rounds is None:
+                from .mlfriends import _bootstrap_rounds as compute_rounds
+            maxd, maxf, failed = 0.0, 0.0, 0.0
+            if hi > lo:
+                maxd_r, f_r, active, failure = compute_rounds(u, unormed, selected, lo, hi, minvol)
+                if failure is not None:
+                    failed, local_exc, message = 1.0, failure[1], str(failure[1])
+                for r in range(lo, hi):
+                    if not active[r]:
+                        continue
+                    if failure is not None and r >= failure[0]:
+                        break
+                    maxd = max(maxd, maxd_r[r])
+                    f = f_r[r]
+                    if not np.isfinite(f) or not f > 0:
+                        failed, message = 1.0, "Distances are not positive"
+                        break
+                    maxf = max(maxf, f)
+            buf = torch.tensor([maxd, maxf, failed, tag, -tag], dtype=torch.float64, device=dev)
+    except Exception as exc:  # noqa: BLE001 -- every rank must still reach the collective
+        local_exc, message = exc, str(exc)
+        buf = torch.tensor([0.0, 0.0, 1.0, tag, -tag], dtype=torch.float64, device=dev)
     # NaN under MAX is implementation-defined in NCCL, so failure travels as its own flag
     # (the reference ships NaN through gather/bcast, integrator.py:391-393, 406-411)
-    r2, f, anyfail = allreduce_max([maxd, maxf, failed])
+    if timings is None:
+        timings = last_timings
+    if dev.type == "cuda":
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=_group)
+        e1.record()
+        r2, f, anyfail, tag_hi, tag_lo = buf.cpu().numpy()
+        timings["collective_us"] = 1e3 * e0.elapsed_time(e1)
+    else:
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=_group)
+        r2, f, anyfail, tag_hi, tag_lo = buf.cpu().numpy()
+    if tag_hi != -tag_lo:
+        raise RuntimeError("the ranks hold different bootstrap selection masks (not replicas of "
+                           "one seeded stream); use masks='broadcast'")
+    if local_exc is not None:
+        raise local_exc
     if anyfail > 0:
         raise np.linalg.LinAlgError(message or "compute_enlargement failed on another rank")
     assert r2 > 0, (r2, u, unormed)

@@ -560,12 +560,12 @@ class MLFriends(object):
             return distributed.reduce_enlargement(self.u, self.unormed, selected, minvol)
         maxd_r, f_r, active, failure = _bootstrap_rounds(self.u, self.unormed, selected, 0,
                                                          nbootstraps, minvol)
-        if failure is not None:
-            _rewind_rounds(rng, state, N, failure[0] + 1)
-            raise failure[1]
+        # the reference interleaves both checks round by round (mlfriends.pyx:1044-1066): a bad f
+        # in a round BEFORE the one whose host algebra failed is what it reports
+        last = nbootstraps if failure is None else failure[0]
         maxd = 0.0
         maxf = 0.0
-        for r in range(nbootstraps):
+        for r in range(last):
             if not active[r]:
                 continue
             maxd = max(maxd, maxd_r[r])
@@ -575,6 +575,9 @@ class MLFriends(object):
                 assert np.isfinite(f), (self.unormed, f)
                 raise np.linalg.LinAlgError("Distances are not positive")
             maxf = max(maxf, f)
+        if failure is not None:
+            _rewind_rounds(rng, state, N, failure[0] + 1)
+            raise failure[1]
         assert maxd > 0, (maxd, self.u, self.unormed)
         assert maxf > 0, (maxf, self.u, self.unormed)
         return maxd, maxf

@@ -39,6 +39,15 @@ def _inplace(a, dtype, name):
     return a
 
 
+def _same_length(n, **arrays):
+    """The reference's typed memoryviews raise on a length mismatch; here it would be an
+    out-of-bounds host copy, so the mirrors check before the engine call."""
+    for name, a in arrays.items():
+        if np.ndim(a) != 1 or len(a) != n:
+            raise ValueError("%s: expected a 1-d array of length %d, got shape %s"
+                             % (name, n, np.shape(a)))
+
+
 def _flags(a):
     a = np.asarray(a)
     if a.dtype not in (np.bool_, np.uint8):
@@ -80,6 +89,11 @@ def evolve_update(acceptable, Lnew, Lmin, search_right, bisecting, currentt, cur
     _inplace(searching_left, bool, "searching_left")
     _inplace(searching_right, bool, "searching_right")
     _inplace(success, bool, "success")
+    _same_length(n, search_right=srm, bisecting=bis, currentt=currentt, current_left=current_left,
+                 current_right=current_right, searching_left=searching_left,
+                 searching_right=searching_right, success=success)
+    if len(Lnew) < int(np.count_nonzero(acc)):
+        raise ValueError("Lnew has %d entries for %d acceptable walkers" % (len(Lnew), np.count_nonzero(acc)))
     if n == 0:
         return
     p = _native._ptr
@@ -114,6 +128,10 @@ def evolve(transform, loglike, Lmin, currentu, currentL, currentt, currentv, cur
     _inplace(searching_left, bool, "searching_left")
     _inplace(searching_right, bool, "searching_right")
     v = _native.as_f64(currentv, 2)
+    _same_length(n, currentt=currentt, current_left=current_left, current_right=current_right,
+                 searching_left=searching_left, searching_right=searching_right)
+    if v.shape != currentu.shape:
+        raise ValueError("currentv %s does not match currentu %s" % (v.shape, currentu.shape))
     # the only random numbers of a step: the bisecting walkers' slice coordinates (:255)
     bisecting = ~(searching_left.astype(bool) | searching_right.astype(bool))
     currentt[bisecting] = np.random.uniform(current_left[bisecting], current_right[bisecting])
@@ -170,8 +188,21 @@ def step_back(Lmin, allL, generation, currentt, log=False):
     _inplace(allL, np.float64, "allL")
     _inplace(generation, np.int64, "generation")
     _inplace(currentt, np.float64, "currentt")
+    if allL.ndim != 2 or generation.shape != (allL.shape[0],) or currentt.shape != (allL.shape[0],):
+        raise ValueError("step_back: allL %s, generation %s, currentt %s do not agree"
+                         % (allL.shape, generation.shape, currentt.shape))
     if allL.size == 0:
         return
+    # allL[i, g] of a walker that has to step back (stepfuncs.pyx:322-327): NumPy raises
+    # IndexError for g outside [-ncols, ncols); check the (rare) offenders like the reference
+    ncols = allL.shape[1]
+    offenders = np.flatnonzero((generation >= ncols) | (generation < -ncols))
+    if len(offenders):
+        max_width = generation.max() + 1
+        for i in offenders:
+            if (allL[i, :max_width] < Lmin).any():
+                raise IndexError("index %d is out of bounds for axis 1 with size %d"
+                                 % (generation[i], ncols))
     p = _native._ptr
     _native.get_engine().call("unb_step_back", float(Lmin), p(allL), allL.shape[0], allL.shape[1],
                               p(generation), p(currentt))
@@ -195,6 +226,11 @@ def update_vectorised_slice_sampler(t, tleft, tright, proposed_L, proposed_u, pr
     if min(len(t), len(tleft), len(tright), len(pL), len(pu), len(pp), len(worker_running),
            len(status), len(allu), len(allL), len(allp)) < popsize:
         raise ValueError("arrays shorter than popsize=%d" % popsize)
+    if pu.ndim != 2 or allu.ndim != 2 or allu.shape[1] != pu.shape[1]:
+        raise ValueError("allu %s does not match proposed_u %s" % (allu.shape, pu.shape))
+    if pp.ndim != 2 or allp.ndim != 2 or allp.shape[1] != pp.shape[1]:
+        raise ValueError("allp %s does not match proposed_p %s" % (allp.shape, pp.shape))
+    _same_length(len(tleft), tright=tright, status=status)
     discarded = np.zeros(1, dtype=np.int64)
     p = _native._ptr
     if popsize:
