@@ -293,6 +293,47 @@ int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t ndim,
                       const unb_refill_desc *desc, uint8_t *flags, double *like,
                       int64_t *counts);
 
+/* ------------------------------------------------ device-side proposal generation
+ * "Throughput mode" of MLFriends.sample (mlfriends.pyx:1162-1184): the draws of
+ * sample_from_wrapping_ellipsoid (mlfriends.pyx:1135-1160) or sample_from_boundingbox
+ * (mlfriends.pyx:1096-1112) are made ON THE DEVICE by a counter-based generator (Philox4x32-10;
+ * key = seed, counter = offset + row), filtered by the region exactly like the host-RNG path
+ * (unit cube, wrapping ellipsoid, neighbour test; optionally the likelihood and `like > Lmin`), and
+ * only the accepted rows are returned, in draw order.  No proposal crosses PCIe on the way in.
+ * NOT the reference's random stream (np.random MT19937): statistically equivalent proposals, a
+ * different seeded sequence; the parity path (host RNG) is the default everywhere. */
+#define UNB_SAMPLE_WRAPPING_ELLIPSOID 0
+#define UNB_SAMPLE_UNIT_CUBE 1
+
+typedef struct unb_sample_desc {
+    int32_t method;             /* UNB_SAMPLE_* */
+    int32_t loglike_kind;       /* UNB_LOGLIKE_*; NONE: no likelihood */
+    int32_t use_lmin;           /* 1: drop rows with like <= Lmin (needs a likelihood) */
+    int32_t reserved;
+    uint64_t seed;              /* generator key */
+    uint64_t offset;            /* global index of the first draw of this call: calls with
+                                   disjoint [offset, offset + nsamples) ranges never overlap */
+    const double *axes_T;       /* [ndim x ndim] MLFriends.ellipsoid_axes_T (WRAPPING_ELLIPSOID) */
+    const double *lparams;      /* as for unb_region_inside_loglike */
+    double Lmin;
+} unb_sample_desc;
+
+/* rows_out: caller-allocated nsamples x ndim; like_out: nsamples or NULL; *n_out = accepted rows;
+ * counts (nullable) = [draws inside the unit cube, region members, accepted]. */
+int unb_region_sample(unb_ctx *ctx, const unb_sample_desc *desc, size_t nsamples, double *rows_out,
+                      double *like_out, int64_t *n_out, int64_t *counts);
+/* device-resident variant: rows_out_dev (nsamples x ndim), like_out_dev (nullable), n_out_dev (one
+ * int32) are DEVICE pointers; only enqueues work on `stream`. */
+int unb_region_sample_dev(unb_ctx *ctx, const unb_sample_desc *desc, size_t nsamples,
+                          double *rows_out_dev, double *like_out_dev, int32_t *n_out_dev,
+                          void *stream);
+/* the raw draws (before any region filter) and their unit-cube mask: lets a test restate the
+ * generator on the host.  center / axes_T / enlarge as MLFriends.ellipsoid_center, .ellipsoid_axes_T,
+ * .enlarge; ignored for UNB_SAMPLE_UNIT_CUBE. */
+int unb_sample_draw(unb_ctx *ctx, int method, size_t nsamples, size_t ndim, uint64_t seed,
+                    uint64_t offset, const double *center, const double *axes_T, double enlarge,
+                    double *rows_out, uint8_t *cube_out);
+
 /* ------------------------------------------------ population step-sampler helpers
  * (SURVEY 8-f rank 2): ultranest/stepfuncs.pyx, the compiled helpers of the vectorised slice
  * samplers in ultranest/popstepsampler.py.  Boolean arrays are NumPy bool (1 byte), integer

@@ -40,6 +40,9 @@ LOGLIKE_GAUSS = 1
 LOGLIKE_EGGBOX = 2
 LOGLIKE_ROSENBROCK = 3
 
+SAMPLE_WRAPPING_ELLIPSOID = 0
+SAMPLE_UNIT_CUBE = 1
+
 XFORM_IDENTITY = 0
 XFORM_SCALE_SHIFT = 1
 REFILL_MEMBER, REFILL_TREGION, REFILL_ACCEPTED = 1, 2, 4
@@ -97,6 +100,10 @@ SIGNATURES = {
     "unb_region_inside_loglike": [_c_vp, _sz, _c_vp, _c_vp, _int, _c_vp],
     "unb_region_inside_loglike_dev": [_c_vp, _sz, _c_vp, _c_vp, _int, _c_vp, _c_vp],
     "unb_region_refill": [_c_vp, _sz, _sz, _c_vp, _c_vp, _c_vp, _c_vp],
+    "unb_region_sample": [_c_vp, _sz, _c_vp, _c_vp, _c_ip, _c_vp],
+    "unb_region_sample_dev": [_c_vp, _sz, _c_vp, _c_vp, _c_vp, _c_vp],
+    "unb_sample_draw": [_int, _sz, _sz, ctypes.c_uint64, ctypes.c_uint64, _c_vp, _c_vp, _dbl, _c_vp,
+                        _c_vp],
     # population step-sampler helpers (ultranest/stepfuncs.pyx)
     "unb_within_unit_cube": [_c_vp, _sz, _sz, _c_vp],
     "unb_evolve_prepare": [_c_vp, _c_vp, _sz, _c_vp, _c_vp],
@@ -487,6 +494,31 @@ class Engine(object):
                   int(kind), _ptr(lp))
         return mask, like
 
+    def region_sample(self, nsamples, ndim, method, seed, offset, axes_T=None, like_kind=LOGLIKE_NONE,
+                      lparams=None, Lmin=None):
+        """Device-generated proposals filtered by the mirrored region (``unb_region_sample``).
+        Returns ``(rows[k, ndim], logl[k] or None)``, accepted rows in draw order."""
+        desc, keep = make_sample_desc(method, seed, offset, axes_T, like_kind, lparams, Lmin)
+        rows = np.empty((int(nsamples), int(ndim)))
+        like = np.empty(int(nsamples)) if like_kind != LOGLIKE_NONE else None
+        n_out = _i64(0)
+        self.call("unb_region_sample", ctypes.addressof(desc), int(nsamples), _ptr(rows), _ptr(like),
+                  ctypes.byref(n_out), None)
+        del keep
+        k = int(n_out.value)
+        return rows[:k], (like[:k] if like is not None else None)
+
+    def sample_draw(self, method, nsamples, ndim, seed, offset, center=None, axes_T=None, enlarge=1.0):
+        """The generator's raw draws and their unit-cube mask (``unb_sample_draw``; for tests)."""
+        rows = np.empty((int(nsamples), int(ndim)))
+        cube = np.empty(int(nsamples), dtype=bool)
+        c = as_f64(center, 1) if center is not None else None
+        a = as_f64(axes_T, 2) if axes_T is not None else None
+        self.call("unb_sample_draw", int(method), int(nsamples), int(ndim),
+                  int(seed) & 0xffffffffffffffff, int(offset) & 0xffffffffffffffff, _ptr(c), _ptr(a),
+                  float(enlarge), _ptr(rows), _ptr(cube))
+        return rows, cube
+
     def region_refill(self, u, region_mode, check_cube, xform, tregion, like_kind, lparams, Lmin):
         """Fused ``_refill_samples`` stage chain (``unb_region_refill``).  ``xform``: ``None`` or
         ``(scale, lo)``; ``tregion``: ``None`` or ``(center, invcov, enlarge)``.  Returns
@@ -528,6 +560,36 @@ class Engine(object):
                   _ptr(like), _ptr(counts))
         del keep
         return flags, like, (int(counts[0]), int(counts[1]), int(counts[2]))
+
+
+class SampleDesc(ctypes.Structure):
+    """``unb_sample_desc`` of include/ultranest_b200.h."""
+    _fields_ = [("method", ctypes.c_int32), ("loglike_kind", ctypes.c_int32),
+                ("use_lmin", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint64),
+                ("axes_T", ctypes.c_void_p), ("lparams", ctypes.c_void_p),
+                ("Lmin", ctypes.c_double)]
+
+
+def make_sample_desc(method, seed, offset, axes_T=None, like_kind=LOGLIKE_NONE, lparams=None, Lmin=None):
+    """``(desc, keepalive)`` for ``unb_region_sample[_dev]``."""
+    keep = []
+    desc = SampleDesc()
+    desc.method = int(method)
+    desc.loglike_kind = int(like_kind)
+    desc.use_lmin = 0 if Lmin is None else 1
+    desc.Lmin = 0.0 if Lmin is None else float(Lmin)
+    desc.seed = int(seed) & 0xffffffffffffffff
+    desc.offset = int(offset) & 0xffffffffffffffff
+    if axes_T is not None:
+        a = as_f64(axes_T, 2)
+        keep.append(a)
+        desc.axes_T = _ptr(a)
+    if lparams is not None:
+        lp = as_f64(lparams)
+        keep.append(lp)
+        desc.lparams = _ptr(lp)
+    return desc, keep
 
 
 class StepDesc(ctypes.Structure):

@@ -316,6 +316,8 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
     free_dev(ctx->boot_idx); free_dev(ctx->boot_meta); free_dev(ctx->boot_out);
     free_dev(ctx->boot_ell);
     free_pin(ctx->pin_small);
+    free_dev(ctx->smp_cube); free_dev(ctx->smp_counts); free_dev(ctx->smp_rows);
+    free_dev(ctx->smp_like); free_dev(ctx->smp_axes); free_dev(ctx->smp_center);
     for (DevBuf &b : ctx->sf) free_dev(b);
     free_dev(ctx->sf_params);
     delete ctx;
@@ -1208,6 +1210,164 @@ extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return unb_fail(ctx, UNB_ERR_CUDA, "refill pipeline: %s", cudaGetErrorString(e));
     for (int i = 0; i < 3; i++) counts[i] = cnt_host[i];
+    return UNB_OK;
+}
+
+// ---- device-side proposal generation (mlfriends.pyx:1096-1112, 1135-1160 without the host RNG) ----
+namespace {
+
+// draw `rows` proposals starting at global index `offset`, filter them and compact the accepted
+// rows (draw order) into out_rows/out_like (device); *n_out_dev receives the count.  All on `s`.
+int sample_enqueue(unb_ctx *ctx, const unb_sample_desc *desc, unsigned long long offset, size_t rows,
+                   double *out_rows_dev, double *out_like_dev, int *n_out_dev, int *counts_dev,
+                   cudaStream_t s)
+{
+    RegionState &R = ctx->region;
+    Lane &ln = ctx->lane[0];
+    const size_t d = R.live.d;
+    const bool want_like = desc->loglike_kind != UNB_LOGLIKE_NONE;
+    UNB_TRY(unb_reserve(ctx, ln.cand, rows * d * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ln.mask, rows));
+    UNB_TRY(unb_reserve(ctx, ctx->smp_cube, rows));
+    if (want_like) UNB_TRY(unb_reserve(ctx, ln.like, rows * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->smp_counts, unb_compact_scratch_ints((long long)rows) * sizeof(int)));
+    UNB_TRY(unb_launch_draw(ctx, desc->method, (long long)rows, (int)d, desc->seed, offset,
+                            (const double *)R.ell_center.p, (const double *)ctx->smp_axes.p,
+                            sqrt(R.enlarge), (double *)ln.cand.p, (unsigned char *)ctx->smp_cube.p, s));
+    // wrapping-ellipsoid draws lie inside the ellipsoid by construction (the reference does not
+    // test it either, mlfriends.pyx:1152-1158); unit-cube draws get the full inside()
+    UNB_TRY(enqueue_inside(ctx, ln, s, (const double *)ln.cand.p, rows, (unsigned char *)ln.mask.p,
+                           nullptr, want_like ? (double *)ln.like.p : nullptr, desc->loglike_kind,
+                           desc->method == UNB_SAMPLE_UNIT_CUBE, false));
+    (void)counts_dev;
+    UNB_TRY(unb_launch_finish_mask(ctx, (unsigned char *)ln.mask.p, (const unsigned char *)ctx->smp_cube.p,
+                                   want_like ? (const double *)ln.like.p : nullptr, desc->Lmin,
+                                   want_like && desc->use_lmin, (long long)rows, s));
+    return unb_launch_compact_rows(ctx, (const unsigned char *)ln.mask.p, (long long)rows, (int)d,
+                                   (const double *)ln.cand.p,
+                                   want_like ? (const double *)ln.like.p : nullptr,
+                                   (int *)ctx->smp_counts.p, n_out_dev, out_rows_dev,
+                                   want_like ? out_like_dev : nullptr, nullptr, s);
+}
+
+int sample_prepare(unb_ctx *ctx, const unb_sample_desc *desc, cudaStream_t s)
+{
+    if (!desc) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (desc->method != UNB_SAMPLE_WRAPPING_ELLIPSOID && desc->method != UNB_SAMPLE_UNIT_CUBE)
+        return unb_fail(ctx, UNB_ERR_ARG, "unknown sampling method %d", desc->method);
+    if (desc->use_lmin && desc->loglike_kind == UNB_LOGLIKE_NONE)
+        return unb_fail(ctx, UNB_ERR_ARG, "the Lmin cut needs a device likelihood");
+    UNB_TRY(region_ready(ctx, true));
+    RegionState &R = ctx->region;
+    const size_t d = R.live.d;
+    if (desc->method == UNB_SAMPLE_WRAPPING_ELLIPSOID) {
+        if (!desc->axes_T) return unb_fail(ctx, UNB_ERR_ARG, "wrapping-ellipsoid draws need axes_T");
+        if (!(R.enlarge > 0.0)) return unb_fail(ctx, UNB_ERR_NUMERIC, "enlarge must be positive");
+        if (ctx->smp_axes_h.size() != d * d ||
+            memcmp(ctx->smp_axes_h.data(), desc->axes_T, d * d * sizeof(double)) != 0) {
+            UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
+            UNB_CUDA(ctx, cudaStreamSynchronize(s));
+            ctx->smp_axes_h.assign(desc->axes_T, desc->axes_T + d * d);
+            UNB_TRY(unb_reserve(ctx, ctx->smp_axes, d * d * sizeof(double)));
+            UNB_TRY(h2d(ctx, ctx->smp_axes.p, ctx->smp_axes_h.data(), d * d * sizeof(double), s));
+            UNB_CUDA(ctx, cudaStreamSynchronize(s));
+        }
+    }
+    if (desc->loglike_kind != UNB_LOGLIKE_NONE && desc->lparams)
+        UNB_TRY(upload_lparams(ctx, desc->loglike_kind, desc->lparams, d, s));
+    return prepare_threshold(ctx, R.live, R.r2, s, nullptr);
+}
+
+}  // namespace
+
+extern "C" int unb_region_sample_dev(unb_ctx *ctx, const unb_sample_desc *desc, size_t nsamples,
+                                     double *rows_out_dev, double *like_out_dev, int32_t *n_out_dev,
+                                     void *stream)
+{
+    UNB_TRY(check_ctx(ctx));
+    cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
+    UNB_TRY(sample_prepare(ctx, desc, s));
+    if (!rows_out_dev || !n_out_dev) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (nsamples > 0x7fffffffULL) return unb_fail(ctx, UNB_ERR_ARG, "too many rows (max 2^31-1 per call)");
+    if (nsamples == 0) {
+        UNB_CUDA(ctx, cudaMemsetAsync(n_out_dev, 0, sizeof(int), s));
+        return UNB_OK;
+    }
+    return sample_enqueue(ctx, desc, desc->offset, nsamples, rows_out_dev, like_out_dev,
+                          (int *)n_out_dev, nullptr, s);
+}
+
+extern "C" int unb_region_sample(unb_ctx *ctx, const unb_sample_desc *desc, size_t nsamples,
+                                 double *rows_out, double *like_out, int64_t *n_out, int64_t *counts)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!n_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    *n_out = 0;
+    if (counts) counts[0] = counts[1] = counts[2] = 0;
+    cudaStream_t s = S0(ctx);
+    UNB_TRY(sample_prepare(ctx, desc, s));
+    if (nsamples == 0) return UNB_OK;
+    if (!rows_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    const size_t d = ctx->region.live.d;
+    const bool want_like = desc->loglike_kind != UNB_LOGLIKE_NONE && like_out;
+    const size_t chunk = std::min<size_t>(nsamples, ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 20));
+    UNB_TRY(unb_reserve(ctx, ctx->smp_rows, chunk * d * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->smp_like, chunk * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->aux3, 4 * sizeof(int)));
+    int *n_dev = (int *)ctx->aux3.p;
+    size_t filled = 0;
+    for (size_t off = 0; off < nsamples; off += chunk) {
+        const size_t rows = std::min(chunk, nsamples - off);
+        UNB_TRY(sample_enqueue(ctx, desc, desc->offset + off, rows, (double *)ctx->smp_rows.p,
+                               (double *)ctx->smp_like.p, n_dev, nullptr, s));
+        int n_acc = 0;
+        UNB_TRY(d2h(ctx, &n_acc, n_dev, sizeof(int), s));
+        UNB_CUDA(ctx, cudaStreamSynchronize(s));
+        if (n_acc > 0) {
+            UNB_TRY(d2h(ctx, rows_out + filled * d, ctx->smp_rows.p, (size_t)n_acc * d * sizeof(double), s));
+            if (want_like)
+                UNB_TRY(d2h(ctx, like_out + filled, ctx->smp_like.p, (size_t)n_acc * sizeof(double), s));
+            UNB_CUDA(ctx, cudaStreamSynchronize(s));
+            filled += (size_t)n_acc;
+        }
+    }
+    *n_out = (int64_t)filled;
+    if (counts) counts[2] = (int64_t)filled;
+    return UNB_OK;
+}
+
+extern "C" int unb_sample_draw(unb_ctx *ctx, int method, size_t nsamples, size_t ndim, uint64_t seed,
+                               uint64_t offset, const double *center, const double *axes_T,
+                               double enlarge, double *rows_out, uint8_t *cube_out)
+{
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, nsamples, ndim));
+    if (nsamples == 0) return UNB_OK;
+    if (!rows_out || !cube_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
+    if (method != UNB_SAMPLE_WRAPPING_ELLIPSOID && method != UNB_SAMPLE_UNIT_CUBE)
+        return unb_fail(ctx, UNB_ERR_ARG, "unknown sampling method %d", method);
+    const size_t d = ndim;
+    cudaStream_t s = S0(ctx);
+    Lane &ln = ctx->lane[0];
+    UNB_TRY(unb_reserve(ctx, ln.cand, nsamples * d * sizeof(double)));
+    UNB_TRY(unb_reserve(ctx, ctx->smp_cube, nsamples));
+    const double *c_dev = nullptr, *a_dev = nullptr;
+    if (method == UNB_SAMPLE_WRAPPING_ELLIPSOID) {
+        if (!center || !axes_T || !(enlarge > 0.0))
+            return unb_fail(ctx, UNB_ERR_ARG, "wrapping-ellipsoid draws need center, axes_T, enlarge > 0");
+        UNB_TRY(unb_reserve(ctx, ctx->smp_center, d * sizeof(double)));
+        UNB_TRY(unb_reserve(ctx, ctx->aux2, d * d * sizeof(double)));
+        UNB_TRY(h2d(ctx, ctx->smp_center.p, center, d * sizeof(double), s));
+        UNB_TRY(h2d(ctx, ctx->aux2.p, axes_T, d * d * sizeof(double), s));
+        c_dev = (const double *)ctx->smp_center.p;
+        a_dev = (const double *)ctx->aux2.p;
+    }
+    UNB_TRY(unb_launch_draw(ctx, method, (long long)nsamples, (int)d, seed, offset, c_dev, a_dev,
+                            method == UNB_SAMPLE_WRAPPING_ELLIPSOID ? sqrt(enlarge) : 1.0,
+                            (double *)ln.cand.p, (unsigned char *)ctx->smp_cube.p, s));
+    UNB_TRY(d2h(ctx, rows_out, ln.cand.p, nsamples * d * sizeof(double), s));
+    UNB_TRY(d2h(ctx, cube_out, ctx->smp_cube.p, nsamples, s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
     return UNB_OK;
 }
 

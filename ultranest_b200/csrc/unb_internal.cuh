@@ -183,6 +183,9 @@ struct unb_ctx {
     // bootstrap scratch
     DevBuf boot_rows, boot_u, boot_tiles, boot_idx, boot_meta, boot_out, boot_ell;
     PinBuf pin_small;
+    // device-side proposal generation (unb_sample.cu)
+    DevBuf smp_cube, smp_counts, smp_rows, smp_like, smp_axes, smp_center;
+    std::vector<double> smp_axes_h;
     // population step-sampler helpers (unb_stepfuncs.cu): scratch buffers + slice-loop session
     DevBuf sf[14];
     DevBuf sf_params;
@@ -276,6 +279,18 @@ int unb_launch_enlargement_f(unb_ctx *ctx, const double *u, int d, const int *it
 int unb_launch_pairdist(unb_ctx *ctx, const double *pts, const long long *ids, int n, int d,
                         double *partial_sum, long long *partial_cnt, cudaStream_t s);
 size_t unb_max_rowwise_d();
+// device-side proposal generation (unb_sample.cu)
+int unb_launch_draw(unb_ctx *ctx, int method, long long m, int d, unsigned long long seed,
+                    unsigned long long offset, const double *center_dev, const double *axes_T_dev,
+                    double scale, double *out_dev, unsigned char *cube_dev, cudaStream_t s);
+int unb_launch_finish_mask(unb_ctx *ctx, unsigned char *mask_dev, const unsigned char *cube_dev,
+                           const double *like_dev, double Lmin, bool use_lmin, long long m,
+                           cudaStream_t s);
+int unb_launch_compact_rows(unb_ctx *ctx, const unsigned char *mask_dev, long long m, int d,
+                            const double *rows_dev, const double *like_dev, int *scratch_counts,
+                            int *total_dev, double *out_rows_dev, double *out_like_dev,
+                            long long *out_index_dev, cudaStream_t s);
+size_t unb_compact_scratch_ints(long long m);
 int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, cudaStream_t s);
 int unb_launch_fp32_peak(unb_ctx *ctx, float *scratch, int blocks, int iters, cudaStream_t s);
 

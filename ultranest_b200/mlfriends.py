@@ -677,9 +677,50 @@ class MLFriends(object):
             self.current_sampling_method = \
                 self.sampling_methods[np.random.randint(len(self.sampling_methods))]
 
+    # -- device-side proposal generation ("throughput mode", NOT the reference's random stream) ----
+    #: set ``region.device_rng = True`` (and optionally ``region.device_seed``) to let
+    #: :meth:`sample` draw its proposals on the device; the default keeps every draw on the host
+    #: ``np.random`` stream in the reference's order (seeded runs identical to the reference's)
+    device_rng = False
+    device_seed = 0
+    _device_draws = 0
+
+    def sample_device(self, nsamples=100, method=None, seed=None, loglike=None, Lmin=None):
+        """``nsamples`` proposals drawn ON THE DEVICE (Philox4x32-10 keyed by ``seed``) and
+        filtered by the region like :meth:`sample_from_wrapping_ellipsoid` (default) or
+        :meth:`sample_from_boundingbox` (``method="boundingbox"``): only accepted rows cross PCIe.
+        With a device likelihood from :mod:`ultranest_b200.likelihoods` returns ``(rows, logl)``
+        (and with ``Lmin`` only rows with ``logl > Lmin``), else ``rows``.  Statistically the
+        reference's proposals (mlfriends.pyx:1096-1112, 1135-1160), not its random stream."""
+        from . import _native, distributed
+        if type(self) is not MLFriends:
+            raise NotImplementedError("device-side proposals are implemented for MLFriends regions")
+        if not self._fused_ok():
+            raise ValueError("device-side proposals need a learned layer without circular dimensions")
+        if method is None:
+            method = getattr(self.current_sampling_method, "__name__", "")
+        unit_cube = "boundingbox" in str(method) and "transformed" not in str(method)
+        N, ndim = self.u.shape
+        if seed is None:
+            seed = self.device_seed
+        # every call (and every rank) consumes its own range of the counter space
+        offset = (distributed.rank() << 44) + self._device_draws
+        self._device_draws += int(nsamples)
+        kind, lparams = (_native.LOGLIKE_NONE, None) if loglike is None else loglike.device_spec(ndim)
+        rows, like = self._bind().region_sample(
+            nsamples, ndim, _native.SAMPLE_UNIT_CUBE if unit_cube else _native.SAMPLE_WRAPPING_ELLIPSOID,
+            seed, offset, None if unit_cube else self.ellipsoid_axes_T, kind, lparams, Lmin)
+        return rows if loglike is None else (rows, like)
+
     def sample(self, nsamples=100):
         """Draw from the region with the current method; switch method at random when a draw
         comes back empty (mlfriends.pyx:1162-1184)."""
+        if self.device_rng and type(self) is MLFriends and self._fused_ok():
+            name = getattr(self.current_sampling_method, "__name__", "")
+            if name in ("sample_from_boundingbox", "sample_from_wrapping_ellipsoid"):
+                samples = self.sample_device(nsamples, method=name)
+                self._after_sample(len(samples))
+                return samples
         samples = self.current_sampling_method(nsamples=nsamples)
         if len(samples) == 0:
             self.current_sampling_method = \
