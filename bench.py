@@ -468,6 +468,36 @@ def run_ours(args):
         rf = eng.region_refill(np_pts, 2, False, None, None, kind, lparams, Lmin)
     refill_ms = 1e3 * (time.perf_counter() - t0) / max(K // 2, 1)
     refill_ok = bool(((rf[0] & 1).astype(bool) == np_mask).all()) and rf[2][2] == int((np_like > Lmin).sum())
+    # throughput mode: the proposals are DRAWN ON THE DEVICE (Philox; not the reference's random
+    # stream), filtered by the region, likelihood + `> Lmin` cut fused, and only the accepted rows
+    # and their likelihoods come back (pinned buffers) -- no H2D at all
+    pin_rows = torch.empty((M, NDIM), dtype=torch.float64).pin_memory()
+    pin_like2 = torch.empty(M, dtype=torch.float64).pin_memory()
+    n_acc = ctypes.c_int64(0)
+    sdesc, skeep = _native.make_sample_desc(_native.SAMPLE_WRAPPING_ELLIPSOID, 20261017 + rank, 0,
+                                            region.ellipsoid_axes_T, kind, lparams, Lmin)
+
+    def rng_step(i):
+        sdesc.offset = i * M
+        eng.call("unb_region_sample", ctypes.addressof(sdesc), M, pin_rows.data_ptr(),
+                 pin_like2.data_ptr(), ctypes.byref(n_acc), None)
+
+    for i in range(W):
+        rng_step(i)
+    barrier()
+    d2h1 = eng.stat(_native.STAT_D2H_BYTES)
+    h2d1 = eng.stat(_native.STAT_H2D_BYTES)
+    t0 = time.perf_counter()
+    for i in range(K):
+        rng_step(W + i)
+    torch.cuda.synchronize()
+    rng_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    rng_d2h = (eng.stat(_native.STAT_D2H_BYTES) - d2h1) // K
+    rng_h2d = (eng.stat(_native.STAT_H2D_BYTES) - h2d1) // K
+    rng_rows = int(n_acc.value)
+    rng_ok = bool(rng_rows > 0 and (pin_like2.numpy()[:rng_rows] > Lmin).all()
+                  and region.inside(pin_rows.numpy()[:min(rng_rows, 4096)]).all())
+    del skeep
     clk = clocks.stop()
     e2e_ok = bool((np_mask.view(np.uint8) == mask_dev.cpu().numpy()).all()) if world == 1 else True
 
@@ -563,7 +593,15 @@ def run_ours(args):
                 "call": "unb_region_inside_loglike (pinned host buffers, chunked double-buffered)",
                 "refill_call": {"ms_per_step": refill_ms, "value": M / (refill_ms * 1e-3),
                                 "matches": refill_ok, "accepted_rows": rf[2][2],
-                                "call": "unb_region_refill (integrator.py:1773-1805 as one pipeline)"}},
+                                "call": "unb_region_refill (integrator.py:1773-1805 as one pipeline)"},
+                "device_rng_call": {"value": world * M * K / (rng_ms * 1e-3), "ms_per_step": rng_ms / K,
+                                    "h2d_bytes_per_step": int(rng_h2d), "d2h_bytes_per_step": int(rng_d2h),
+                                    "accepted_rows_last_step": rng_rows, "checks_ok": rng_ok,
+                                    "parity": "NON-PARITY random stream: proposals drawn on the device "
+                                              "(Philox4x32-10), statistically the reference's "
+                                              "sample_from_wrapping_ellipsoid; same region filter, "
+                                              "likelihood and logl > Lmin cut (Lmin = median)",
+                                    "call": "unb_region_sample (opt-in: region.device_rng = True)"}},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clk,

@@ -164,10 +164,32 @@ double orc_mean_pair_distance(const double *pts, const int64_t *clusterids, size
     return total_dist / npairs;
 }
 
+/* The quadratic form of np.einsum('ij,jk,ik->i', delta, A, delta) for one row, in NumPy's order:
+ * acc += (delta_j * A_jk) * delta_k, j outer, k inner, sequential, no FMA -- and
+ * NumPy reduces through its buffered iterator (np.getbufsize() = 8192 elements): the partial sum
+ * restarts every floor(8192 / ndim) rows j and the partials are added to the result in order.
+ * Up to ndim = 90 that is the plain sequential sum; from 91 on the chunking shows in the last bits
+ * (probed bitwise against the compiled reference for ndim in {2 ... 150}). */
+static double orc_einsum_quadform(const double *delta, const double *a, size_t ndim)
+{
+    size_t rows = 8192 / ndim;
+    if (rows < 1) rows = 1;
+    double total = 0.0;
+    for (size_t j0 = 0; j0 < ndim; j0 += rows) {
+        size_t j1 = j0 + rows < ndim ? j0 + rows : ndim;
+        double acc = 0.0;
+        for (size_t j = j0; j < j1; j++)
+            for (size_t k = 0; k < ndim; k++)
+                acc = acc + (delta[j] * a[j * ndim + k]) * delta[k];
+        total = total + acc;
+    }
+    return total;
+}
+
 /* _inside_ellipsoid: mlfriends.pyx:882-912.  d = points - center (rounded), then
  * np.einsum('ij,jk,ik->i', d, invcov, d), whose accumulation order on NumPy >= 1.2x
- * is  acc += (d_j * A_jk) * d_k,  j outer, k inner, sequential, no FMA
- * (probed 100 % bitwise for d in {2,5,20,50}); mask = r <= square_radius.
+ * is  acc += (d_j * A_jk) * d_k,  j outer, k inner, sequential, no FMA, in buffered chunks
+ * (orc_einsum_quadform above); mask = r <= square_radius.
  * r_out may be NULL. */
 void orc_inside_ellipsoid(const double *points, size_t m, size_t ndim,
                           const double *center, const double *invcov,
@@ -177,10 +199,7 @@ void orc_inside_ellipsoid(const double *points, size_t m, size_t ndim,
     for (size_t p = 0; p < m; p++) {
         for (size_t k = 0; k < ndim; k++)
             delta[k] = points[p * ndim + k] - center[k];
-        double acc = 0.0;
-        for (size_t j = 0; j < ndim; j++)
-            for (size_t k = 0; k < ndim; k++)
-                acc = acc + (delta[j] * invcov[j * ndim + k]) * delta[k];
+        double acc = orc_einsum_quadform(delta, invcov, ndim);
         if (r_out) r_out[p] = acc;
         mask[p] = (acc <= square_radius) ? 1 : 0;
     }
@@ -328,10 +347,7 @@ double orc_enlargement_f(const double *u, size_t n, size_t ndim, const uint8_t *
         if (selected[p]) continue;
         for (size_t k = 0; k < ndim; k++)
             delta[k] = u[p * ndim + k] - ctr[k];
-        double acc = 0.0;
-        for (size_t j = 0; j < ndim; j++)
-            for (size_t k = 0; k < ndim; k++)
-                acc = acc + (delta[j] * a[j * ndim + k]) * delta[k];
+        double acc = orc_einsum_quadform(delta, a, ndim);
         if (acc > f) f = acc;
     }
     return f;

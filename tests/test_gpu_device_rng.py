@@ -102,7 +102,8 @@ def test_accepted_rows_equal_the_host_filter_of_the_raw_draws(eng):
     from ultranest_b200 import _native
     from ultranest_b200 import mlfriends as ml
     from ultranest_b200.likelihoods import GaussianLogLike
-    u = bench.make_live(1500, 6, seed=3)
+    u = 0.5 + (bench.make_live(1500, 6, seed=3) - 0.5) * 7.0    # wide: the unit cube cuts it
+    assert (u > 0).all() and (u < 1).all()
     layer = ml.AffineLayer()
     layer.optimize(u, u)
     region = ml.MLFriends(u, layer)

@@ -73,6 +73,7 @@ def test_config4_mlfriends_n4000_d100(eng):
     layer = ml.AffineLayer()
     layer.optimize(u, u)
     region = ml.MLFriends(u, layer)
+    # (d > 90: the enlargement's einsum follows NumPy's buffered reduction, chunks of 8192 // d rows)
     got = region.compute_enlargement(nbootstraps=3, rng=np.random.RandomState(2))
     want = cport.compute_enlargement(u, region.unormed, 3, np.random.RandomState(2))
     assert got == want

@@ -101,7 +101,7 @@ def test_compute_maxradiussq_bootstrap_bitexact(ref, n, d):
     assert np.float32(r) == r  # float32-representable
 
 
-@pytest.mark.parametrize("n,d", [(400, 5), (800, 20)])
+@pytest.mark.parametrize("n,d", [(400, 5), (800, 20), (600, 100)])
 def test_compute_enlargement_bitexact(ref, n, d):
     rng = np.random.RandomState(13)
     u = rng.uniform(0.3, 0.7, size=(n, d))
@@ -121,10 +121,11 @@ def test_mean_pair_distance_bitexact(ref):
     assert cport.mean_pair_distance(pts, ids) == ref.compute_mean_pair_distance(pts, ids)
 
 
-@pytest.mark.parametrize("d", [1, 2, 5, 20, 50])
+@pytest.mark.parametrize("d", [1, 2, 5, 20, 50, 90, 91, 100, 128, 150])
 def test_inside_ellipsoid_bitexact(ref, d):
     rng = np.random.RandomState(19 + d)
-    pts = rng.uniform(size=(2000, d))
+    # d > 90: NumPy's buffered einsum restarts its partial sum every 8192 // d rows
+    pts = rng.uniform(size=(2000 if d <= 50 else 400, d))
     ctr = rng.uniform(0.4, 0.6, size=d)
     A = rng.normal(size=(d, d))
     invcov = A @ A.T / d + np.eye(d)

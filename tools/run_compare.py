@@ -2,7 +2,8 @@
 """Whole-run comparison: the reference's UNMODIFIED ReactiveNestedSampler (oracle/_ref) on the same
 seeded problem with (a) its own Cython region module on the host, (b) ultranest_b200 installed
 behind the same names, (c) additionally the likelihood on the device and the fused
-``_refill_samples``.  Each arm runs in its own process; the runs must be the same run
+``_refill_samples``, (d) additionally the exact fast ``MultiCounter`` (ultranest_b200.netiter).
+Each arm runs in its own process; the runs must be the same run
 (niter, ncall, logZ), so the wall-clock ratio is the end-to-end effect of the drop-in.
 
     python tools/run_compare.py [--ndim 20] [--nlive 4000] [--max-ncalls 8000]
@@ -26,12 +27,15 @@ def arm(mode, ndim, nlive, max_ncalls, sigma):
         import ultranest_b200
         ultranest_b200.install(force=True)
     from ultranest import ReactiveNestedSampler
+    if mode == "full":   # + the exact fast MultiCounter
+        import ultranest_b200
+        ultranest_b200.install(force=True, netiter=True)
 
     def numpy_loglike(theta):
         return -0.5 * (((theta - 0.5) / sigma)**2).sum(axis=1) - 0.5 * np.log(2 * np.pi * sigma**2) * ndim
 
     loglike, transform = numpy_loglike, (lambda x: x)
-    if mode == "device":
+    if mode in ("device", "full"):
         from ultranest_b200.likelihoods import GaussianLogLike
         from ultranest_b200.transforms import IdentityTransform
         loglike, transform = GaussianLogLike(0.5, sigma), IdentityTransform()
@@ -39,7 +43,7 @@ def arm(mode, ndim, nlive, max_ncalls, sigma):
     sampler = ReactiveNestedSampler(["p%d" % i for i in range(ndim)], loglike, transform=transform,
                                     log_dir=None, vectorized=True)
     stats = None
-    if mode == "device":
+    if mode in ("device", "full"):
         from ultranest_b200 import refill
         stats = refill.attach(sampler)
     t0 = time.perf_counter()
@@ -62,7 +66,7 @@ def main():
     ap.add_argument("--max-ncalls", type=int, default=8000)
     ap.add_argument("--sigma", type=float, default=0.05)
     ap.add_argument("--arm", default=None)
-    ap.add_argument("--arms", default="reference,ours,device")
+    ap.add_argument("--arms", default="reference,ours,device,full")
     args = ap.parse_args()
     if args.arm:
         return arm(args.arm, args.ndim, args.nlive, args.max_ncalls, args.sigma)

@@ -19,15 +19,20 @@ Beyond the region: :mod:`ultranest_b200.refill` fuses ``_refill_samples`` into o
 (``refill.attach(sampler)``), :mod:`ultranest_b200.stepfuncs` / :mod:`ultranest_b200.popstepsampler`
 put the compiled helpers of the population step samplers (``ultranest/stepfuncs.pyx``) and the
 inner loop of ``PopulationSimpleSliceSampler`` on the device (``install(stepfuncs=True)``,
-``popstepsampler.attach(stepsampler)``).
+``popstepsampler.attach(stepsampler)``); :mod:`ultranest_b200.netiter` is an exact, faster
+``MultiCounter.passing_node`` (``install(netiter=True)``).
 """
 import sys
 
 __version__ = "0.1.0"
 
 
-def install(force=False, stepfuncs=False):
+def install(force=False, stepfuncs=False, netiter=False):
     """Make ``import ultranest.mlfriends`` resolve to :mod:`ultranest_b200.mlfriends`.
+
+    ``netiter=True`` also rebinds ``MultiCounter`` to the exact, faster subclass of
+    :mod:`ultranest_b200.netiter` (its ``passing_node`` is what is left of a run once the region
+    is on the GPU; the run stays bit-identical).
 
     ``stepfuncs=True`` also rebinds the step-sampler helpers ``ultranest.popstepsampler`` imported
     by name (``evolve``, ``step_back``, ``update_vectorised_slice_sampler``, the direction
@@ -64,6 +69,9 @@ def install(force=False, stepfuncs=False):
     if stepfuncs:
         from . import stepfuncs as ours_steps
         _step_undo.extend(ours_steps.install())
+    if netiter:
+        from . import netiter as ours_netiter
+        ours_netiter.install()
     return ours
 
 

@@ -300,7 +300,10 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
         Lane &ln = ctx->lane[i];
         free_dev(ln.cand); free_dev(ln.tcand); free_dev(ln.items); free_dev(ln.counter);
         free_dev(ln.mask); free_dev(ln.idx); free_dev(ln.like);
+        free_dev(ln.smp_cube); free_dev(ln.smp_counts); free_dev(ln.smp_rows); free_dev(ln.smp_like);
+        free_dev(ln.smp_n);
         free_pin(ln.pin_in); free_pin(ln.pin_mask); free_pin(ln.pin_like); free_pin(ln.pin_idx);
+        free_pin(ln.pin_n);
         if (ln.ev_in) cudaEventDestroy(ln.ev_in);
         if (ln.ev_done) cudaEventDestroy(ln.ev_done);
         if (ln.stream) cudaStreamDestroy(ln.stream);
@@ -316,8 +319,7 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
     free_dev(ctx->boot_idx); free_dev(ctx->boot_meta); free_dev(ctx->boot_out);
     free_dev(ctx->boot_ell);
     free_pin(ctx->pin_small);
-    free_dev(ctx->smp_cube); free_dev(ctx->smp_counts); free_dev(ctx->smp_rows);
-    free_dev(ctx->smp_like); free_dev(ctx->smp_axes); free_dev(ctx->smp_center);
+    free_dev(ctx->smp_axes); free_dev(ctx->smp_center);
     for (DevBuf &b : ctx->sf) free_dev(b);
     free_dev(ctx->sf_params);
     delete ctx;
@@ -1217,36 +1219,35 @@ extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t
 namespace {
 
 // draw `rows` proposals starting at global index `offset`, filter them and compact the accepted
-// rows (draw order) into out_rows/out_like (device); *n_out_dev receives the count.  All on `s`.
-int sample_enqueue(unb_ctx *ctx, const unb_sample_desc *desc, unsigned long long offset, size_t rows,
-                   double *out_rows_dev, double *out_like_dev, int *n_out_dev, int *counts_dev,
+// rows (draw order) into out_rows/out_like (device); *n_out_dev receives the count.  All on `s`,
+// with the scratch buffers of lane `ln`.
+int sample_enqueue(unb_ctx *ctx, Lane &ln, const unb_sample_desc *desc, unsigned long long offset,
+                   size_t rows, double *out_rows_dev, double *out_like_dev, int *n_out_dev,
                    cudaStream_t s)
 {
     RegionState &R = ctx->region;
-    Lane &ln = ctx->lane[0];
     const size_t d = R.live.d;
     const bool want_like = desc->loglike_kind != UNB_LOGLIKE_NONE;
     UNB_TRY(unb_reserve(ctx, ln.cand, rows * d * sizeof(double)));
     UNB_TRY(unb_reserve(ctx, ln.mask, rows));
-    UNB_TRY(unb_reserve(ctx, ctx->smp_cube, rows));
+    UNB_TRY(unb_reserve(ctx, ln.smp_cube, rows));
     if (want_like) UNB_TRY(unb_reserve(ctx, ln.like, rows * sizeof(double)));
-    UNB_TRY(unb_reserve(ctx, ctx->smp_counts, unb_compact_scratch_ints((long long)rows) * sizeof(int)));
+    UNB_TRY(unb_reserve(ctx, ln.smp_counts, unb_compact_scratch_ints((long long)rows) * sizeof(int)));
     UNB_TRY(unb_launch_draw(ctx, desc->method, (long long)rows, (int)d, desc->seed, offset,
                             (const double *)R.ell_center.p, (const double *)ctx->smp_axes.p,
-                            sqrt(R.enlarge), (double *)ln.cand.p, (unsigned char *)ctx->smp_cube.p, s));
+                            sqrt(R.enlarge), (double *)ln.cand.p, (unsigned char *)ln.smp_cube.p, s));
     // wrapping-ellipsoid draws lie inside the ellipsoid by construction (the reference does not
     // test it either, mlfriends.pyx:1152-1158); unit-cube draws get the full inside()
     UNB_TRY(enqueue_inside(ctx, ln, s, (const double *)ln.cand.p, rows, (unsigned char *)ln.mask.p,
                            nullptr, want_like ? (double *)ln.like.p : nullptr, desc->loglike_kind,
                            desc->method == UNB_SAMPLE_UNIT_CUBE, false));
-    (void)counts_dev;
-    UNB_TRY(unb_launch_finish_mask(ctx, (unsigned char *)ln.mask.p, (const unsigned char *)ctx->smp_cube.p,
+    UNB_TRY(unb_launch_finish_mask(ctx, (unsigned char *)ln.mask.p, (const unsigned char *)ln.smp_cube.p,
                                    want_like ? (const double *)ln.like.p : nullptr, desc->Lmin,
                                    want_like && desc->use_lmin, (long long)rows, s));
     return unb_launch_compact_rows(ctx, (const unsigned char *)ln.mask.p, (long long)rows, (int)d,
                                    (const double *)ln.cand.p,
                                    want_like ? (const double *)ln.like.p : nullptr,
-                                   (int *)ctx->smp_counts.p, n_out_dev, out_rows_dev,
+                                   (int *)ln.smp_counts.p, n_out_dev, out_rows_dev,
                                    want_like ? out_like_dev : nullptr, nullptr, s);
 }
 
@@ -1293,8 +1294,8 @@ extern "C" int unb_region_sample_dev(unb_ctx *ctx, const unb_sample_desc *desc, 
         UNB_CUDA(ctx, cudaMemsetAsync(n_out_dev, 0, sizeof(int), s));
         return UNB_OK;
     }
-    return sample_enqueue(ctx, desc, desc->offset, nsamples, rows_out_dev, like_out_dev,
-                          (int *)n_out_dev, nullptr, s);
+    return sample_enqueue(ctx, ctx->lane[0], desc, desc->offset, nsamples, rows_out_dev, like_out_dev,
+                          (int *)n_out_dev, s);
 }
 
 extern "C" int unb_region_sample(unb_ctx *ctx, const unb_sample_desc *desc, size_t nsamples,
@@ -1310,27 +1311,47 @@ extern "C" int unb_region_sample(unb_ctx *ctx, const unb_sample_desc *desc, size
     if (!rows_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     const size_t d = ctx->region.live.d;
     const bool want_like = desc->loglike_kind != UNB_LOGLIKE_NONE && like_out;
-    const size_t chunk = std::min<size_t>(nsamples, ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 20));
-    UNB_TRY(unb_reserve(ctx, ctx->smp_rows, chunk * d * sizeof(double)));
-    UNB_TRY(unb_reserve(ctx, ctx->smp_like, chunk * sizeof(double)));
-    UNB_TRY(unb_reserve(ctx, ctx->aux3, 4 * sizeof(int)));
-    int *n_dev = (int *)ctx->aux3.p;
+    // chunks alternate between the two lanes: the kernels of chunk c+1 run while the accepted rows
+    // of chunk c travel back.  The row copy of a chunk needs its count, hence the per-chunk sync of
+    // that lane only.
+    const size_t chunk = std::min<size_t>(nsamples, ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));   // sample_prepare ran on lane 0's stream
+    for (int i = 0; i < 2; i++) {
+        Lane &ln = ctx->lane[i];
+        UNB_TRY(unb_reserve(ctx, ln.smp_rows, chunk * d * sizeof(double)));
+        UNB_TRY(unb_reserve(ctx, ln.smp_like, chunk * sizeof(double)));
+        UNB_TRY(unb_reserve(ctx, ln.smp_n, 4 * sizeof(int)));
+        UNB_TRY(unb_reserve_pinned(ctx, ln.pin_n, 4 * sizeof(int)));
+    }
     size_t filled = 0;
-    for (size_t off = 0; off < nsamples; off += chunk) {
-        const size_t rows = std::min(chunk, nsamples - off);
-        UNB_TRY(sample_enqueue(ctx, desc, desc->offset + off, rows, (double *)ctx->smp_rows.p,
-                               (double *)ctx->smp_like.p, n_dev, nullptr, s));
-        int n_acc = 0;
-        UNB_TRY(d2h(ctx, &n_acc, n_dev, sizeof(int), s));
-        UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    const size_t nchunks = (nsamples + chunk - 1) / chunk;
+    auto launch = [&](size_t c) -> int {
+        Lane &ln = ctx->lane[c & 1];
+        const size_t off = c * chunk, rows = std::min(chunk, nsamples - off);
+        UNB_TRY(sample_enqueue(ctx, ln, desc, desc->offset + off, rows, (double *)ln.smp_rows.p,
+                               (double *)ln.smp_like.p, (int *)ln.smp_n.p, ln.stream));
+        return d2h(ctx, ln.pin_n.p, ln.smp_n.p, sizeof(int), ln.stream);
+    };
+    auto collect = [&](size_t c) -> int {
+        Lane &ln = ctx->lane[c & 1];
+        UNB_CUDA(ctx, cudaStreamSynchronize(ln.stream));
+        const int n_acc = *(const int *)ln.pin_n.p;
         if (n_acc > 0) {
-            UNB_TRY(d2h(ctx, rows_out + filled * d, ctx->smp_rows.p, (size_t)n_acc * d * sizeof(double), s));
+            UNB_TRY(d2h(ctx, rows_out + filled * d, ln.smp_rows.p, (size_t)n_acc * d * sizeof(double), ln.stream));
             if (want_like)
-                UNB_TRY(d2h(ctx, like_out + filled, ctx->smp_like.p, (size_t)n_acc * sizeof(double), s));
-            UNB_CUDA(ctx, cudaStreamSynchronize(s));
+                UNB_TRY(d2h(ctx, like_out + filled, ln.smp_like.p, (size_t)n_acc * sizeof(double), ln.stream));
             filled += (size_t)n_acc;
         }
+        return UNB_OK;
+    };
+    UNB_TRY(launch(0));
+    for (size_t c = 1; c < nchunks; c++) {
+        UNB_TRY(launch(c));
+        UNB_TRY(collect(c - 1));
     }
+    UNB_TRY(collect(nchunks - 1));
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
+    UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
     *n_out = (int64_t)filled;
     if (counts) counts[2] = (int64_t)filled;
     return UNB_OK;
@@ -1350,7 +1371,7 @@ extern "C" int unb_sample_draw(unb_ctx *ctx, int method, size_t nsamples, size_t
     cudaStream_t s = S0(ctx);
     Lane &ln = ctx->lane[0];
     UNB_TRY(unb_reserve(ctx, ln.cand, nsamples * d * sizeof(double)));
-    UNB_TRY(unb_reserve(ctx, ctx->smp_cube, nsamples));
+    UNB_TRY(unb_reserve(ctx, ln.smp_cube, nsamples));
     const double *c_dev = nullptr, *a_dev = nullptr;
     if (method == UNB_SAMPLE_WRAPPING_ELLIPSOID) {
         if (!center || !axes_T || !(enlarge > 0.0))
@@ -1364,9 +1385,9 @@ extern "C" int unb_sample_draw(unb_ctx *ctx, int method, size_t nsamples, size_t
     }
     UNB_TRY(unb_launch_draw(ctx, method, (long long)nsamples, (int)d, seed, offset, c_dev, a_dev,
                             method == UNB_SAMPLE_WRAPPING_ELLIPSOID ? sqrt(enlarge) : 1.0,
-                            (double *)ln.cand.p, (unsigned char *)ctx->smp_cube.p, s));
+                            (double *)ln.cand.p, (unsigned char *)ln.smp_cube.p, s));
     UNB_TRY(d2h(ctx, rows_out, ln.cand.p, nsamples * d * sizeof(double), s));
-    UNB_TRY(d2h(ctx, cube_out, ctx->smp_cube.p, nsamples, s));
+    UNB_TRY(d2h(ctx, cube_out, ln.smp_cube.p, nsamples, s));
     UNB_CUDA(ctx, cudaStreamSynchronize(s));
     return UNB_OK;
 }

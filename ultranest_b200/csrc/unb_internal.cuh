@@ -151,7 +151,8 @@ struct Lane {
     cudaEvent_t ev_in = nullptr;    // H2D from pin_in finished
     cudaEvent_t ev_done = nullptr;  // everything of the chunk finished
     DevBuf cand, tcand, items, counter, mask, idx, like;
-    PinBuf pin_in, pin_mask, pin_like, pin_idx;
+    DevBuf smp_cube, smp_counts, smp_rows, smp_like, smp_n;   // device-side proposal generation
+    PinBuf pin_in, pin_mask, pin_like, pin_idx, pin_n;
     // deferred copy-out of a staged result
     unsigned char *pend_mask = nullptr;
     double *pend_like = nullptr;
@@ -184,7 +185,7 @@ struct unb_ctx {
     DevBuf boot_rows, boot_u, boot_tiles, boot_idx, boot_meta, boot_out, boot_ell;
     PinBuf pin_small;
     // device-side proposal generation (unb_sample.cu)
-    DevBuf smp_cube, smp_counts, smp_rows, smp_like, smp_axes, smp_center;
+    DevBuf smp_axes, smp_center;
     std::vector<double> smp_axes_h;
     // population step-sampler helpers (unb_stepfuncs.cu): scratch buffers + slice-loop session
     DevBuf sf[14];
@@ -367,6 +368,32 @@ __device__ __forceinline__ double sq_step(double acc, double a, double b)
 {
     double diff = __dsub_rn(a, b);
     return __dadd_rn(acc, __dmul_rn(diff, diff));
+}
+
+// np.einsum('ij,jk,ik->i', delta, A, delta) of the reference (mlfriends.pyx:910, 1062, 1432):
+// acc += (delta_j * A_jk) * delta_k, j outer, k inner, no FMA -- and, because NumPy reduces through
+// its BUFFERED iterator (np.getbufsize() = 8192 elements), the partial sum restarts every
+// floor(8192 / d) rows j and the partials are added to the result in order.  For d <= 90 that is
+// the plain sequential sum; beyond, the chunking changes the last bits (probed against the compiled
+// reference at d = 91 ... 150, tests/test_oracle_vs_reference.py).  `A` may be global or constant.
+__device__ __forceinline__ double einsum_quadform(const double *delta, const double *__restrict__ A,
+                                                  int d)
+{
+    int rows = 8192 / d;
+    if (rows < 1) rows = 1;
+    double total = 0.0;
+    for (int j0 = 0; j0 < d; j0 += rows) {
+        const int j1 = (j0 + rows < d) ? j0 + rows : d;
+        double acc = 0.0;
+        for (int jj = j0; jj < j1; jj++) {
+            const double dj = delta[jj];
+            const double *Arow = A + (size_t)jj * d;
+            for (int k = 0; k < d; k++)
+                acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), delta[k]));
+        }
+        total = __dadd_rn(total, acc);
+    }
+    return total;
 }
 
 // Packed single-precision FMA (Blackwell FFMA2): d.x = a.x*b.x + c.x, d.y = a.y*b.y + c.y, each

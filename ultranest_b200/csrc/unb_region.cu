@@ -66,13 +66,8 @@ __global__ void k_prep(const PrepArgs P)
             const double *p = P.pts + j * d;
             for (int k = 0; k < d; k++)
                 my[k] = __dsub_rn(p[k], __ldg(P.center + k));
-            // np.einsum('ij,jk,ik->i'): acc += (d_j * A_jk) * d_k, j outer, k inner
-            for (int jj = 0; jj < d; jj++) {
-                const double dj = my[jj];
-                const double *Arow = P.invcov + (size_t)jj * d;
-                for (int k = 0; k < d; k++)
-                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
-            }
+            // np.einsum('ij,jk,ik->i'): acc += (d_j * A_jk) * d_k, j outer, k inner (buffered chunks)
+            acc = einsum_quadform(my, P.invcov, d);
         }
         inside = valid && (acc <= P.r2);
         if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
@@ -457,14 +452,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_prep_tile(const PrepArgs P)
             bool in = rfast <= P.r2;
             const bool band = !(fabs(__dsub_rn(rfast, P.r2)) > tol);   // also true for NaN
             if (band && valid) {
-                double acc = 0.0;
-                for (int jj = 0; jj < d; jj++) {
-                    const double dj = my[jj];
-                    const double *Arow = P.invcov + (size_t)jj * d;
-                    for (int k = 0; k < d; k++)
-                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), my[k]));
-                }
-                in = acc <= P.r2;
+                in = einsum_quadform(my, P.invcov, d) <= P.r2;
             }
             inside = valid && in;
             if (valid && P.mask) P.mask[j] = inside ? 1 : 0;
@@ -617,14 +605,7 @@ __global__ void k_refill_tail(const TailArgs T)
             tpass = true;
             if (T.treg_center) {
                 for (int k = 0; k < d; k++) t[k] = __dsub_rn(v[k], __ldg(T.treg_center + k));
-                double acc = 0.0;
-                for (int jj = 0; jj < d; jj++) {
-                    const double dj = t[jj];
-                    const double *Arow = T.treg_invcov + (size_t)jj * d;
-                    for (int k = 0; k < d; k++)
-                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(Arow + k)), t[k]));
-                }
-                tpass = acc <= T.treg_r2;
+                tpass = einsum_quadform(t, T.treg_invcov, d) <= T.treg_r2;
             }
             if (tpass) {
                 like = loglike_row(T.loglike_kind, v, d, t, T.lparams);
@@ -668,13 +649,7 @@ __global__ void k_enlargement_f(const double *__restrict__ u, int d,
         const double *ctr = ctrs + (size_t)round * d;
         const double *A = invcovs + (size_t)round * d * d;
         for (int k = 0; k < d; k++) my[k] = __dsub_rn(p[k], __ldg(ctr + k));
-        double acc = 0.0;
-        for (int jj = 0; jj < d; jj++) {
-            const double dj = my[jj];
-            for (int k = 0; k < d; k++)
-                acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dj, __ldg(A + (size_t)jj * d + k)), my[k]));
-        }
-        key = f64_key(acc);
+        key = f64_key(einsum_quadform(my, A, d));
     }
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long other = __shfl_xor_sync(FULL, key, o);
