@@ -621,6 +621,216 @@ def run_ours(args):
     return 0
 
 
+# --------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (not the driver's headline line): --config 2|3|4
+# --------------------------------------------------------------------------------------
+def run_config(args):
+    """One JSON line for BASELINE.json configs[2], [3] or [4] at N GPUs (torchrun for N > 1):
+    rows / rounds sharded over the ranks, device-timed `value`, warmed host-buffer `e2e`."""
+    import ctypes
+    import torch
+    from ultranest_b200 import _native
+    from ultranest_b200 import distributed as D
+    from ultranest_b200 import mlfriends as ours
+    from ultranest_b200.likelihoods import RosenbrockLogLike
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = _native.get_engine()
+    K, W = args.steps, max(args.warmup, 3)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sh = ctypes.c_void_p(stream.cuda_stream)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def dev_timed(fn):
+        for _ in range(W):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            fn()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / K
+
+    def host_timed(fn):
+        for _ in range(W):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            fn()
+        torch.cuda.synchronize()
+        return max_over_ranks(1e3 * (time.perf_counter() - t0)) / K
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        t.numpy()[...] = a
+        return t
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    line = {"n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    if args.config == 2:
+        # eggbox-like 10-D, N_live=2000: the 30-round bootstrapped radius + enlargement, rounds
+        # sharded over the ranks, ONE NCCL allreduce(MAX) per rebuild (integrator.py:388-404)
+        u = multimodal_live()
+        region, ms_1, res_1 = time_rebuild(ours, u, reps=5)
+        rec = {"rebuild_ms_1rank": ms_1, "r2": float(res_1[0]), "f": float(res_1[1])}
+        ms = ms_1
+        if dist is not None:
+            D.enable()
+            times, colls = [], []
+            for _ in range(W + K):
+                barrier()
+                t0 = time.perf_counter()
+                res_s = region.compute_enlargement(nbootstraps=NBOOT, rng=np.random.RandomState(2))
+                times.append(max_over_ranks(1e3 * (time.perf_counter() - t0)))
+                colls.append(max_over_ranks(D.last_timings.get("collective_us", 0.0)))
+            D.disable()
+            ms = float(np.median(times[W:]))
+            rec.update({"rebuild_ms_sharded": ms, "collective_us": float(np.median(colls[W:])),
+                        "identical_to_1rank": bool(res_s == res_1)})
+        line.update({"metric": "region rebuilds/sec (30-round bootstrapped max-radius + enlargement), eggbox-like N_live=2000 d=10",
+                     "value": 1e3 / ms, "unit": "rebuilds/s", "ms_per_step": ms,
+                     "config": {"workload": "BASELINE configs[2]: eggbox-like 10-D live set, N_live=2000, "
+                                            "bootstrap rounds sharded over %d GPU(s), one allreduce(MAX)" % world,
+                                "n_live": 2000, "ndim": 10, "nbootstraps": NBOOT},
+                     "rebuild": rec, "gpu_launches": int(eng.stat(_native.STAT_KERNEL_LAUNCHES))})
+    elif args.config == 3:
+        # 50-D, N_live=8000 RobustEllipsoidRegion: Mahalanobis filter + Rosenbrock batch likelihood
+        n, d, M = 8000, 50, args.batch // 4
+        u = make_live(n, d, seed=1)
+        layer = ours.AffineLayer()
+        layer.optimize(u, u)
+        region = ours.RobustEllipsoidRegion(u, layer)
+        region.maxradiussq, region.enlarge = region.compute_enlargement(nbootstraps=NBOOT, rng=np.random.RandomState(2))
+        region.create_ellipsoid()
+        cand = make_candidates(region, M, 3 + rank)
+        loglike = RosenbrockLogLike()
+        mask0 = region.inside(cand)
+        c_dev = torch.from_numpy(cand).cuda()
+        m_dev = torch.empty(M, dtype=torch.uint8, device="cuda")
+        l_dev = torch.empty(M, dtype=torch.float64, device="cuda")
+        launches0 = eng.stat(_native.STAT_KERNEL_LAUNCHES)
+
+        def dev_step():
+            eng.call("unb_region_inside_ellipsoid_dev", c_dev.data_ptr(), M, m_dev.data_ptr(), sh)
+            eng.call("unb_loglike_rosenbrock_dev", c_dev.data_ptr(), d, M, l_dev.data_ptr(), m_dev.data_ptr(), sh)
+
+        have_dev_like = hasattr(eng.lib, "unb_loglike_rosenbrock_dev")
+        if not have_dev_like:
+            def dev_step():   # noqa: F811 -- filter alone (the likelihood has no _dev entry point)
+                eng.call("unb_region_inside_ellipsoid_dev", c_dev.data_ptr(), M, m_dev.data_ptr(), sh)
+        dev_ms = dev_timed(dev_step)
+        launches = (eng.stat(_native.STAT_KERNEL_LAUNCHES) - launches0) // (K + W)
+        pin = pinned(cand)
+        h2d0, d2h0 = eng.stat(_native.STAT_H2D_BYTES), eng.stat(_native.STAT_D2H_BYTES)
+
+        def e2e_step():
+            m = region.inside(pin.numpy())
+            return loglike(pin.numpy()[m] * 20 - 10) if args.with_loglike else m
+
+        e2e_ms = host_timed(e2e_step)
+        steps_run = K + W
+        alg = M * (8.0 * d + 1.0)
+        line.update({"metric": "proposed-points/sec through RobustEllipsoidRegion.inside (Mahalanobis filter), N_live=8000 d=50",
+                     "value": world * M / (dev_ms * 1e-3), "unit": "points/s", "ms_per_step": dev_ms,
+                     "config": {"workload": "BASELINE configs[3]: 50-D, N_live=8000, RobustEllipsoidRegion "
+                                            "(ellipsoid filter alone), wrapping-ellipsoid proposals; rows sharded over %d GPU(s)" % world,
+                                "n_live": n, "ndim": d, "rows_per_step_per_gpu": M,
+                                "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU)" % (M * d * 8 / 1e6),
+                                "device_step": "filter + Rosenbrock likelihood" if have_dev_like else "filter"},
+                     "e2e": {"value": world * M / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
+                             "h2d_bytes_per_step": int((eng.stat(_native.STAT_H2D_BYTES) - h2d0) // steps_run),
+                             "d2h_bytes_per_step": int((eng.stat(_native.STAT_D2H_BYTES) - d2h0) // steps_run),
+                             "call": "RobustEllipsoidRegion.inside(pinned host rows)" + (" + RosenbrockLogLike" if args.with_loglike else "")},
+                     "roofline": {"bound": "hbm", "kernel": "k_prep_tile (ellipsoid filter, d=50)",
+                                  "achieved": alg / (dev_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": alg / (dev_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                  "note": "whole device step; algorithmic bytes = 8d+1 per proposal"},
+                     "details": {"accept_fraction": float(mask0.mean()), "enlarge": region.enlarge},
+                     "gpu_launches": int(launches)})
+    else:
+        # membership microbench: M proposals x N_live=4000 x d in {5, 20, 100}; accepting (A) and
+        # full-scan (R) regimes; device-resident and through the host API (pinned t-space rows)
+        cases = []
+        for d in (5, 20, 100):
+            M = args.batch if d <= 20 else args.batch // 8
+            u = make_live(N_LIVE, d, seed=1)
+            layer = ours.AffineLayer()
+            layer.optimize(u, u)
+            region = ours.MLFriends(u, layer)
+            region.maxradiussq, region.enlarge = region.compute_enlargement(nbootstraps=NBOOT, rng=np.random.RandomState(2))
+            region.create_ellipsoid()
+            region._bind()
+            cand = make_candidates(region, M, 3 + rank)
+            rng = np.random.RandomState(4 + rank)
+            r = region.maxradiussq**0.5
+            tbox = rng.uniform(region.bbox_lo - r, region.bbox_hi + r, size=(M, d))
+            for regime, tpts in (("A", region.transformLayer.transform(cand)), ("R", tbox)):
+                tpts = np.ascontiguousarray(tpts)
+                t_dev = torch.from_numpy(tpts).cuda()
+                mask = torch.empty(M, dtype=torch.uint8, device="cuda")
+                ms_any = dev_timed(lambda: eng.call("unb_region_find_nearby_dev", t_dev.data_ptr(), M,
+                                                    None, mask.data_ptr(), sh))
+                tile_units = eng.stat(_native.STAT_TILE_VISITS)
+                pin = pinned(tpts)
+                ms_host = host_timed(lambda: eng.region_has_neighbour(pin.numpy()))
+                alg = M * (8.0 * d + 1.0) + N_LIVE * d * 8.0
+                cases.append({"ndim": d, "regime": regime, "rows_per_gpu": M,
+                              "accept": float(mask.float().mean().item()),
+                              "ms_device": ms_any, "points_per_s": world * M / (ms_any * 1e-3),
+                              "hbm_gbs": alg / (ms_any * 1e-3) / 1e9, "hbm_frac": alg / (ms_any * 1e-3) / 1e9 / hbm_peak,
+                              "filter_lane_fma_per_s": tile_units * 32.0 * 64.0 * d / (ms_any * 1e-3),
+                              "ms_host_api": ms_host, "points_per_s_host_api": world * M / (ms_host * 1e-3)})
+        head = [c for c in cases if c["ndim"] == 20 and c["regime"] == "R"][0]
+        line.update({"metric": "membership-test candidates/sec, 10^6 candidates x 4000 live x d in {5,20,100}",
+                     "value": head["points_per_s"], "unit": "points/s", "ms_per_step": head["ms_device"],
+                     "config": {"workload": "BASELINE configs[4]: membership microbench, N_live=4000, d in {5,20,100}, "
+                                            "accepting (A) and full-scan (R) regimes; `value` = d=20 full-scan; rows sharded over %d GPU(s)" % world,
+                                "n_live": N_LIVE, "l2_policy": "inputs larger than L2 except d=5 (42 MB)"},
+                     "cases": cases, "hbm_peak_gbs": hbm_peak,
+                     "gpu_launches": int(eng.stat(_native.STAT_KERNEL_LAUNCHES))})
+    line["clocks"] = clocks.stop()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -629,9 +839,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="proposals per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs[k]; 1 (default) is the headline the driver runs")
+    ap.add_argument("--with-loglike", action="store_true", help="--config 3: add the likelihood to the e2e step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != 1:
+        return run_config(args)
     return run_ours(args)
 
 
