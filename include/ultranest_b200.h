@@ -55,6 +55,12 @@ extern "C" {
 #define UNB_OPT_BLOCK_KERNEL 6   /* 1: always the block-synchronous membership kernel, also for
                                     small launches (default 0: warp-independent kernel there)  */
 
+#define UNB_OPT_BIN_MIN_ROWS 7    /* membership launches of at least this many proposals against the
+                                    region's live block use clustered live tiles and proposals binned
+                                    by nearest tile centroid (default 0 = never: on B200 the binning
+                                    passes cost more than the scan gains).  Scheduling only: masks
+                                    do not depend on it                                          */
+
 /* unb_ctx_get_stat keys */
 #define UNB_STAT_KERNEL_LAUNCHES 1   /* kernels launched by this ctx since creation       */
 #define UNB_STAT_RECHECKS 2          /* filtered-scan pairs that went to the exact path

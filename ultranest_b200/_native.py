@@ -25,6 +25,7 @@ OPT_FILTER_FP32 = 3
 OPT_SURE_LEVEL = 4
 OPT_COOP_MAX = 5
 OPT_BLOCK_KERNEL = 6
+OPT_BIN_MIN_ROWS = 7
 STAT_KERNEL_LAUNCHES = 1
 STAT_RECHECKS = 2
 STAT_H2D_BYTES = 3

@@ -84,6 +84,7 @@ void free_pin(PinBuf &b)
 void free_live(LiveTiles &L)
 {
     free_dev(L.tiles); free_dev(L.rows); free_dev(L.norms); free_dev(L.namax); free_dev(L.tiles32);
+    free_dev(L.perm32); free_dev(L.ctiles32); free_dev(L.cl_scratch_i); free_dev(L.cl_scratch_f);
     L.valid = false;
 }
 
@@ -192,10 +193,38 @@ int prepare_threshold(unb_ctx *ctx, LiveTiles &L, double r2, cudaStream_t s, Sca
     if (!ok32) L.t32_valid = false;   // never leave a stale image that looks usable
     if (a && ok32) {
         a->tiles32 = (const float *)L.tiles32.p;
+        a->perm32 = L.t32_clustered ? (const int *)L.perm32.p : nullptr;
         a->kappa32 = unb_kappa32(L.d);
         a->namax32 = sure_namax(ctx, L);
     }
     return UNB_OK;
+}
+
+// large launches against clustered fp32 tiles: bin the work items by nearest tile centroid
+// (unb_cluster.cu) so that the membership kernel starts every proposal where hits are likely
+int attach_bins(unb_ctx *ctx, Lane &ln, const LiveTiles &L, ScanArgs &a, cudaStream_t s)
+{
+    if (!a.tiles32 || !a.perm32 || !L.t32_clustered || ctx->exact_only || ctx->bin_min_rows <= 0 ||
+        a.n_items < ctx->bin_min_rows || L.dr > 32 || a.out_idx)
+        return UNB_OK;
+    const int ntiles = (int)((L.n + 63) / 64);
+    UNB_TRY(unb_reserve(ctx, ln.bin_of, (size_t)a.n_items * sizeof(int)));
+    UNB_TRY(unb_reserve(ctx, ln.bin_order, (size_t)a.n_items * sizeof(int)));
+    UNB_TRY(unb_reserve(ctx, ln.bin_meta, (size_t)(4 * ntiles + 2) * sizeof(int)));
+    int *meta = (int *)ln.bin_meta.p;
+    UNB_TRY(unb_launch_bin_items(ctx, a.cand, a.d, a.dr, a.item_idx, a.n_items_dev, a.n_items,
+                                 (const float *)L.ctiles32.p, ntiles, (int *)ln.bin_of.p,
+                                 (int *)ln.bin_order.p, meta, s));
+    a.bin_order = (const int *)ln.bin_order.p;
+    a.bin_start = meta + ntiles;
+    a.bin_head = meta + ntiles + (ntiles + 1) + ntiles;
+    return UNB_OK;
+}
+
+// a launch of `m` proposals against the region's live block: ask for clustered tiles when large
+void request_cluster(unb_ctx *ctx, LiveTiles &L, size_t m)
+{
+    if (ctx->bin_min_rows > 0 && (long long)m >= ctx->bin_min_rows) L.want_cluster = true;
 }
 
 // upload a live block into L and build its tiles
@@ -278,6 +307,11 @@ extern "C" int unb_ctx_create(int device, unb_ctx **out)
     if (!ctx) return UNB_ERR_NOMEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    // clustered tiles + binned proposals are OPT-IN (UNB_OPT_BIN_MIN_ROWS): measured on B200 they
+    // halve the tiles a proposal streams (192k -> 90k warp-tiles per 2^20 proposals) but the binning
+    // passes (0.12 + 0.17 ms) cost more than the membership kernel gains (0.49 -> 0.40 ms); see
+    // DESIGN.md 4.1 "Tried, measured, not enabled"
+    ctx->bin_min_rows = 0;
     for (int i = 0; i < 2; i++) {
         Lane &ln = ctx->lane[i];
         if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -302,6 +336,7 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
         free_dev(ln.mask); free_dev(ln.idx); free_dev(ln.like);
         free_dev(ln.smp_cube); free_dev(ln.smp_counts); free_dev(ln.smp_rows); free_dev(ln.smp_like);
         free_dev(ln.smp_n);
+        free_dev(ln.bin_of); free_dev(ln.bin_order); free_dev(ln.bin_meta);
         free_pin(ln.pin_in); free_pin(ln.pin_mask); free_pin(ln.pin_like); free_pin(ln.pin_idx);
         free_pin(ln.pin_n);
         if (ln.ev_in) cudaEventDestroy(ln.ev_in);
@@ -341,6 +376,7 @@ extern "C" int unb_ctx_set_option(unb_ctx *ctx, int option, int64_t value)
     case UNB_OPT_SURE_LEVEL: ctx->sure_level = value ? 1 : 0; return UNB_OK;
     case UNB_OPT_COOP_MAX: ctx->coop_max = value < 0 ? 0 : (int)(value > 1 << 20 ? 1 << 20 : value); return UNB_OK;
     case UNB_OPT_BLOCK_KERNEL: ctx->block_kernel = value ? 1 : 0; return UNB_OK;
+    case UNB_OPT_BIN_MIN_ROWS: ctx->bin_min_rows = value > 0 ? value : 0; return UNB_OK;
     default: return unb_fail(ctx, UNB_ERR_ARG, "unknown option %d", option);
     }
 }
@@ -899,8 +935,10 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
         a.out_like = fuse_like ? like_dev : nullptr;
         if (have32) {
             a.tiles32 = (const float *)R.live.tiles32.p;   // prepared by the caller (set_h stage)
+            a.perm32 = R.live.t32_clustered ? (const int *)R.live.perm32.p : nullptr;
             a.kappa32 = unb_kappa32(R.live.d);
             a.namax32 = sure_namax(ctx, R.live);
+            UNB_TRY(attach_bins(ctx, ln, R.live, a, s));
         }
         UNB_TRY(unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s));
     } else {
@@ -948,10 +986,13 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
     RegionState &R = ctx->region;
     const size_t d = ellipsoid_only ? R.ell_d : R.live.d;
     const size_t rowb = d * sizeof(double);
-    if (!ellipsoid_only) UNB_TRY(prepare_threshold(ctx, R.live, R.r2, S0(ctx), nullptr));
-    UNB_CUDA(ctx, cudaStreamSynchronize(S0(ctx)));
     size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18);
     if (chunk > m) chunk = m;
+    if (!ellipsoid_only) {
+        request_cluster(ctx, R.live, chunk);
+        UNB_TRY(prepare_threshold(ctx, R.live, R.r2, S0(ctx), nullptr));
+    }
+    UNB_CUDA(ctx, cudaStreamSynchronize(S0(ctx)));
     const bool src_pinned = host_is_pinned(pts);
     const bool mask_pinned = host_is_pinned(mask);
     const bool like_pinned = like ? host_is_pinned(like) : true;
@@ -1126,12 +1167,15 @@ extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t
     }
     int *cnt_dev = (int *)(P + nparam);
     UNB_CUDA(ctx, cudaMemsetAsync(cnt_dev, 0, 4 * sizeof(int), s0));
-    if (desc->region_mode != 0) UNB_TRY(prepare_threshold(ctx, R.live, R.r2, s0, nullptr));
-    UNB_CUDA(ctx, cudaStreamSynchronize(s0));
-
     const size_t rowb = d * sizeof(double);
     size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18);
     if (chunk > m) chunk = m;
+    if (desc->region_mode != 0) {
+        request_cluster(ctx, R.live, chunk);
+        UNB_TRY(prepare_threshold(ctx, R.live, R.r2, s0, nullptr));
+    }
+    UNB_CUDA(ctx, cudaStreamSynchronize(s0));
+
     const bool src_pinned = host_is_pinned(u);
     const bool flags_pinned = host_is_pinned(flags);
     const bool like_pinned = host_is_pinned(like);
@@ -1251,7 +1295,7 @@ int sample_enqueue(unb_ctx *ctx, Lane &ln, const unb_sample_desc *desc, unsigned
                                    want_like ? out_like_dev : nullptr, nullptr, s);
 }
 
-int sample_prepare(unb_ctx *ctx, const unb_sample_desc *desc, cudaStream_t s)
+int sample_prepare(unb_ctx *ctx, const unb_sample_desc *desc, size_t nsamples_hint, cudaStream_t s)
 {
     if (!desc) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     if (desc->method != UNB_SAMPLE_WRAPPING_ELLIPSOID && desc->method != UNB_SAMPLE_UNIT_CUBE)
@@ -1276,6 +1320,7 @@ int sample_prepare(unb_ctx *ctx, const unb_sample_desc *desc, cudaStream_t s)
     }
     if (desc->loglike_kind != UNB_LOGLIKE_NONE && desc->lparams)
         UNB_TRY(upload_lparams(ctx, desc->loglike_kind, desc->lparams, d, s));
+    request_cluster(ctx, R.live, nsamples_hint);
     return prepare_threshold(ctx, R.live, R.r2, s, nullptr);
 }
 
@@ -1287,7 +1332,7 @@ extern "C" int unb_region_sample_dev(unb_ctx *ctx, const unb_sample_desc *desc, 
 {
     UNB_TRY(check_ctx(ctx));
     cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
-    UNB_TRY(sample_prepare(ctx, desc, s));
+    UNB_TRY(sample_prepare(ctx, desc, nsamples, s));
     if (!rows_out_dev || !n_out_dev) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     if (nsamples > 0x7fffffffULL) return unb_fail(ctx, UNB_ERR_ARG, "too many rows (max 2^31-1 per call)");
     if (nsamples == 0) {
@@ -1306,7 +1351,8 @@ extern "C" int unb_region_sample(unb_ctx *ctx, const unb_sample_desc *desc, size
     *n_out = 0;
     if (counts) counts[0] = counts[1] = counts[2] = 0;
     cudaStream_t s = S0(ctx);
-    UNB_TRY(sample_prepare(ctx, desc, s));
+    UNB_TRY(sample_prepare(ctx, desc,
+                           std::min<size_t>(nsamples, ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18)), s));
     if (nsamples == 0) return UNB_OK;
     if (!rows_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     const size_t d = ctx->region.live.d;
@@ -1399,6 +1445,7 @@ extern "C" int unb_region_inside_dev(unb_ctx *ctx, const double *pts_dev, size_t
     UNB_TRY(region_ready(ctx, true));
     if (m == 0) return UNB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
+    request_cluster(ctx, ctx->region.live, m);
     UNB_TRY(prepare_threshold(ctx, ctx->region.live, ctx->region.r2, s, nullptr));
     return enqueue_inside(ctx, ctx->lane[0], s, pts_dev, m, mask_dev, nullptr, nullptr,
                           UNB_LOGLIKE_NONE);
@@ -1413,6 +1460,7 @@ extern "C" int unb_region_inside_loglike_dev(unb_ctx *ctx, const double *pts_dev
     if (m == 0) return UNB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
     if (lparams) UNB_TRY(upload_lparams(ctx, loglike_kind, lparams, ctx->region.live.d, s));
+    request_cluster(ctx, ctx->region.live, m);
     UNB_TRY(prepare_threshold(ctx, ctx->region.live, ctx->region.r2, s, nullptr));
     return enqueue_inside(ctx, ctx->lane[0], s, pts_dev, m, mask_dev, nullptr, like_dev,
                           loglike_kind);
@@ -1447,6 +1495,7 @@ int has_neighbour_host(unb_ctx *ctx, LiveTiles &L, const double *tpts, size_t m,
     UNB_TRY(stat_reset(ctx, s));
     ScanArgs a = scan_args_for(L);
     a.tiles32 = pre.tiles32;
+    a.perm32 = pre.perm32;     // clustered fp32 tiles: slot -> live row (must travel with tiles32)
     a.kappa32 = pre.kappa32;
     a.namax32 = pre.namax32;
     a.cand = (const double *)ln.cand.p;
@@ -1498,10 +1547,12 @@ extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, 
     cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
     ScanArgs pre;
     memset(&pre, 0, sizeof(pre));
+    if (!nnearby_dev) request_cluster(ctx, ctx->region.live, m);
     UNB_TRY(prepare_threshold(ctx, ctx->region.live, ctx->region.r2, s, &pre));
     ScanArgs a = scan_args_for(ctx->region.live);
     if (!nnearby_dev) {
         a.tiles32 = pre.tiles32;
+        a.perm32 = pre.perm32;
         a.kappa32 = pre.kappa32;
         a.namax32 = pre.namax32;
     }
@@ -1518,6 +1569,7 @@ extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, 
     UNB_TRY(stat_reset(ctx, s));
     a.stat_rechecks = (unsigned long long *)ctx->stat.p;
     a.stat_tiles = (unsigned long long *)ctx->stat.p + 1;
+    UNB_TRY(attach_bins(ctx, ln, ctx->region.live, a, s));
     return unb_launch_inside_any(ctx, a, (int *)ln.counter.p + 1, s);
 }
 

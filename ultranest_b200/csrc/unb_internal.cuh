@@ -68,6 +68,12 @@ struct LiveTiles {
     bool t32_valid = false;
     double t32_r2 = 0.0;
     double namax_host = 0.0;   // max squared norm, fetched when the fp32 tiles are built
+    // locality (unb_cluster.cu): the fp32 tiles may hold the live points in CLUSTER order
+    // (perm32: tile slot -> live row) with one centroid per tile (ctiles32, tile layout)
+    bool want_cluster = false;     // requested by a large membership launch on the region's block
+    bool cluster_valid = false;    // perm32 / ctiles32 describe the current rows
+    bool t32_clustered = false;    // tiles32 was built through perm32
+    DevBuf perm32, ctiles32, cl_scratch_i, cl_scratch_f;
 };
 
 enum { HMODE_NONE = -1, HMODE_THRESH = 0, HMODE_MIN = 1 };
@@ -86,6 +92,11 @@ struct ScanArgs {
     // live side
     const double *tiles;      // tiled live block (of this launch / of round 0); NULL -> exact kernel
     const float *tiles32;     // fp32 tiles (membership kernel with the fp32 pre-filter), nullable
+    const int *perm32;        // nullable: fp32 tile slot -> live row (clustered tiles)
+    // proposals binned by nearest tile centroid (nullable: one global work queue instead)
+    const int *bin_order;     // work items sorted by bin
+    const int *bin_start;     // [ntiles + 1]
+    int *bin_head;            // [ntiles] claimed so far (device counters, zeroed per launch)
     double kappa32;           // slack factor of the fp32 filter
     int coop_max;             // block membership kernel: survivors at which the drain turns cooperative
     double namax32;           // max squared norm of the live block (certain-neighbour level); +inf: off
@@ -152,6 +163,7 @@ struct Lane {
     cudaEvent_t ev_done = nullptr;  // everything of the chunk finished
     DevBuf cand, tcand, items, counter, mask, idx, like;
     DevBuf smp_cube, smp_counts, smp_rows, smp_like, smp_n;   // device-side proposal generation
+    DevBuf bin_of, bin_order, bin_meta;                       // proposals binned by nearest tile centroid
     PinBuf pin_in, pin_mask, pin_like, pin_idx, pin_n;
     // deferred copy-out of a staged result
     unsigned char *pend_mask = nullptr;
@@ -173,6 +185,7 @@ struct unb_ctx {
     int sure_level = 1;      // UNB_OPT_SURE_LEVEL
     int coop_max = -1;       // UNB_OPT_COOP_MAX (-1: the kernel's default)
     int block_kernel = 0;    // UNB_OPT_BLOCK_KERNEL
+    long long bin_min_rows = 1 << 17;   // UNB_OPT_BIN_MIN_ROWS: launches from this size on use clustered tiles + bins
     long long chunk_rows = 0;
 
     Lane lane[2];
@@ -280,6 +293,15 @@ int unb_launch_enlargement_f(unb_ctx *ctx, const double *u, int d, const int *it
 int unb_launch_pairdist(unb_ctx *ctx, const double *pts, const long long *ids, int n, int d,
                         double *partial_sum, long long *partial_cnt, cudaStream_t s);
 size_t unb_max_rowwise_d();
+// clustered live tiles + binned proposals (unb_cluster.cu)
+size_t unb_cluster_max_tiles();
+int unb_launch_cluster_live(unb_ctx *ctx, const double *rows, int n, int d, int K, int *perm,
+                            int *scratch_i, float *scratch_f, cudaStream_t s);
+int unb_launch_tile_centroids(unb_ctx *ctx, const double *rows, const int *perm, int n, int d, int dr,
+                              int ntiles, float *ctiles, cudaStream_t s);
+int unb_launch_bin_items(unb_ctx *ctx, const double *cand, int d, int dr, const int *item_idx,
+                         const int *n_items_dev, long long n_items, const float *ctiles, int ntiles,
+                         int *bin_of, int *order, int *meta, cudaStream_t s);
 // device-side proposal generation (unb_sample.cu)
 int unb_launch_draw(unb_ctx *ctx, int method, long long m, int d, unsigned long long seed,
                     unsigned long long offset, const double *center_dev, const double *axes_T_dev,

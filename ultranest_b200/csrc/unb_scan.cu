@@ -781,6 +781,36 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
     }
     bool exhausted = false;
 
+    // one work item into slot m of this thread
+    auto load_item = [&](int m, int item) {
+        const int r = A.item_idx ? A.item_idx[item] : item;
+        row[m] = r;
+        orow[m] = A.out_row_idx ? A.out_row_idx[item] : r;
+        double nb = 0.0;
+#pragma unroll
+        for (int k = 0; k < DR; k++) {
+            const double v = (k < d) ? A.cand[(size_t)r * d + k] : 0.0;
+            a[m][k] = __double2float_rn(v);
+            nb = fma(v, v, nb);
+        }
+        // threshold rounded DOWN; a zero / out-of-range norm flags everything.
+        // thr_hi = thr + M rounded UP: the certain-neighbour level (tile_filter32)
+        const float thr = __double2float_rd(__dmul_rn(nb, thr_scale));
+        const bool in_range = nb < 1e30 && thr > 0.f;
+        thr_lo[m] = in_range ? thr : -__int_as_float(0x7f800000);
+        thr_hi[m] = in_range ? __double2float_ru(__dadd_rn(
+                                   (double)thr, __dmul_rn(sure_scale, __dadd_rn(sure_base, nb))))
+                             : __int_as_float(0x7f800000);
+        rem[m] = ntiles;
+        hit[m] = 0;
+    };
+
+    // binned launches (unb_cluster.cu): the items are sorted by the live tile whose centroid is
+    // nearest, and a warp about to stream tile `cur_bin` takes its new items from that bin (the
+    // following bins when it is empty) -- most proposals then meet a neighbour in their first tile
+    const bool binned = A.bin_order != nullptr;
+    int cur_bin = 0;
+
     auto refill = [&]() {
 #pragma unroll
         for (int m = 0; m < TM; m++) {
@@ -790,44 +820,56 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                 row[m] = -1;
                 thr_lo[m] = __int_as_float(0x7f800000);
             }
-            const bool need = (row[m] < 0) && !exhausted;
-            const unsigned ball = __ballot_sync(FULL, need);
-            if (ball) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(queue_head, __popc(ball));
-                base = __shfl_sync(FULL, base, 0);
-                if (need) {
-                    const int item = base + __popc(ball & ((1u << lane) - 1));
-                    if (item < n_items) {
-                        const int r = A.item_idx ? A.item_idx[item] : item;
-                        row[m] = r;
-                        orow[m] = A.out_row_idx ? A.out_row_idx[item] : r;
-                        double nb = 0.0;
-#pragma unroll
-                        for (int k = 0; k < DR; k++) {
-                            const double v = (k < d) ? A.cand[(size_t)r * d + k] : 0.0;
-                            a[m][k] = __double2float_rn(v);
-                            nb = fma(v, v, nb);
-                        }
-                        // threshold rounded DOWN; a zero / out-of-range norm flags everything.
-                        // thr_hi = thr + M rounded UP: the certain-neighbour level (tile_filter32)
-                        const float thr = __double2float_rd(__dmul_rn(nb, thr_scale));
-                        const bool in_range = nb < 1e30 && thr > 0.f;
-                        thr_lo[m] = in_range ? thr : -__int_as_float(0x7f800000);
-                        thr_hi[m] = in_range ? __double2float_ru(__dadd_rn(
-                                                   (double)thr, __dmul_rn(sure_scale, __dadd_rn(sure_base, nb))))
-                                             : __int_as_float(0x7f800000);
-                        rem[m] = ntiles;
-                        hit[m] = 0;
-                    } else {
-                        exhausted = true;
+            bool need = (row[m] < 0) && !exhausted;
+            unsigned ball = __ballot_sync(FULL, need);
+            if (!binned) {
+                if (ball) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(queue_head, __popc(ball));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (need) {
+                        const int item = base + __popc(ball & ((1u << lane) - 1));
+                        if (item < n_items) load_item(m, item);
+                        else exhausted = true;
                     }
+                }
+            } else {
+                while (ball) {   // warp-uniform
+                    int base = -1, avail = 0, b = cur_bin;
+                    if (lane == 0) {
+                        const int want = __popc(ball);
+                        for (int tries = 0; tries < ntiles; tries++) {
+                            const int size_b = A.bin_start[b + 1] - A.bin_start[b];
+                            if (*(volatile int *)(A.bin_head + b) < size_b) {
+                                const int got = atomicAdd(A.bin_head + b, want);
+                                if (got < size_b) {
+                                    base = got;
+                                    avail = min(want, size_b - got);
+                                    break;
+                                }
+                            }
+                            b = (b + 1 == ntiles) ? 0 : b + 1;
+                        }
+                    }
+                    base = __shfl_sync(FULL, base, 0);
+                    avail = __shfl_sync(FULL, avail, 0);
+                    b = __shfl_sync(FULL, b, 0);
+                    if (base < 0) {   // every bin is empty
+                        exhausted = true;
+                        break;
+                    }
+                    if (need && __popc(ball & ((1u << lane) - 1)) < avail) {
+                        load_item(m, A.bin_order[A.bin_start[b] + base + __popc(ball & ((1u << lane) - 1))]);
+                        need = false;
+                    }
+                    ball = __ballot_sync(FULL, need);
                 }
             }
         }
         exhausted = __any_sync(FULL, exhausted);
     };
 
+    if (binned) cur_bin = (int)(blockIdx.x % (unsigned)ntiles);   // blocks spread over the tiles
     refill();
     {
         bool idle = true;
@@ -836,7 +878,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
         if (__syncthreads_and(idle)) return;
     }
 
-    // block-dependent start tile (see k_inside_any)
+    // block-dependent start tile (see k_inside_any); binned launches start at their first bin
     if (tid == 0) s_info[8] = orow[0] >= 0 ? orow[0] : 0;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -844,8 +886,9 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
         mbar_fence_init();
     }
     __syncthreads();
-    const unsigned start =
-        (unsigned)(((long long)s_info[8] * ntiles) / (A.n_items > 0 ? A.n_items : 1)) % (unsigned)ntiles;
+    const unsigned start = binned
+        ? blockIdx.x % (unsigned)ntiles
+        : (unsigned)(((long long)s_info[8] * ntiles) / (A.n_items > 0 ? A.n_items : 1)) % (unsigned)ntiles;
     if (tid == 0) {
         mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
         tma_bulk_g2s(tbuf, tiles + (size_t)(start % ntiles) * TILE_FLOATS, TILE_BYTES, &bars[0]);
@@ -883,7 +926,8 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                         // padded slots of the last tile are only ever flagged by a proposal that
                         // flags everything (out-of-range norm): they are no live points
                         if (tile_first + col >= A.n_live) continue;
-                        const double *lp = A.live_rows + (size_t)(tile_first + col) * d;
+                        const int lrow = A.perm32 ? A.perm32[tile_first + col] : tile_first + col;
+                        const double *lp = A.live_rows + (size_t)lrow * d;
                         const double *cp = A.cand + (size_t)row[m] * d;
                         // loads are issued in batches of 2 x 12 so that one L2 round trip covers
                         // a batch (the rows are L2 resident); padded terms add +0
@@ -910,6 +954,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
             }
 #pragma unroll
             for (int m = 0; m < TM; m++) rem[m]--;
+            cur_bin = (int)((start + tt + 1) % (unsigned)ntiles);   // the tile this warp streams next
             refill();
         }
         int mine = 0;
@@ -1019,7 +1064,8 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
 #pragma unroll 1
                             for (int which = 0; which < 2; which++) {
                                 if ((which == 0 ? f0 : f1) && !ok && first2 + 2 * lane + which < A.n_live) {
-                                    const double *lp = A.live_rows + (size_t)(first2 + 2 * lane + which) * d;
+                                    const int lslot = first2 + 2 * lane + which;
+                                    const double *lp = A.live_rows + (size_t)(A.perm32 ? A.perm32[lslot] : lslot) * d;
                                     double D = 0.0;
                                     for (int kk = 0; kk < d; kk++) D = sq_step(D, __ldg(lp + kk), __ldg(cp + kk));
                                     ok = D <= A.r2;
@@ -1243,7 +1289,8 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
                     pend[m] &= pend[m] - 1ull;
                     rechecks++;
                     if (tile_first + col >= A.n_live) continue;   // padded slot, no live point
-                    const double *lp = A.live_rows + (size_t)(tile_first + col) * d;
+                    const int lrow = A.perm32 ? A.perm32[tile_first + col] : tile_first + col;
+                    const double *lp = A.live_rows + (size_t)lrow * d;
                     const double *cp = A.cand + (size_t)row[m] * d;
                     double D = 0.0;
 #pragma unroll
@@ -1327,20 +1374,21 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
 // fp32 image of the live block, always in 64-point tiles (independent of the fp64 tile size):
 // coordinates rounded to nearest, h row for radius r2 rounded UP
 __global__ void k_live_build32(const double *__restrict__ rows, const double *__restrict__ norms,
-                               int n, int d, int dr, int ntiles, double r2, double kappa32,
-                               float *__restrict__ tiles32)
+                               const int *__restrict__ perm, int n, int d, int dr, int ntiles,
+                               double r2, double kappa32, float *__restrict__ tiles32)
 {
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= ntiles * REG_TILE_N) return;
     int t = slot / REG_TILE_N, c = slot - t * REG_TILE_N;
     float *F = tiles32 + (size_t)t * (dr + 1) * REG_TILE_N + c;
+    const int src = (slot < n) ? (perm ? perm[slot] : slot) : -1;   // clustered tiles: slot -> live row
     for (int k = 0; k < dr; k++)
         F[(size_t)k * REG_TILE_N] =
-            (slot < n && k < d) ? __double2float_rn(rows[(size_t)slot * d + k]) : 0.f;
+            (src >= 0 && k < d) ? __double2float_rn(rows[(size_t)src * d + k]) : 0.f;
     float h = -1e30f;
     if (slot < n) {
         const double r2w = __dmul_rn(r2, __dadd_rn(1.0, kappa32));
-        const double naw = __dmul_rn(norms[slot], __dsub_rn(1.0, kappa32));
+        const double naw = __dmul_rn(norms[src], __dsub_rn(1.0, kappa32));
         h = __double2float_ru(__dmul_rn(0.5, __dsub_rn(r2w, naw)));
     }
     F[(size_t)dr * REG_TILE_N] = h;
@@ -1682,7 +1730,7 @@ int launch_any32(unb_ctx *ctx, const ScanArgs &a, int *queue_head, cudaStream_t 
     // measured 0.127 vs 0.150 ms at 4096 proposals, 333 vs 428 us per integrator iteration); the
     // block-synchronous kernel wins on bulk launches (block-wide drain compaction, 4x less tile
     // traffic; 0.66 vs 0.71 ms at 2^20).  Per-warp tile buffers also need d <= 32.
-    if (!blocksync && DR <= 32 && a.n_items <= 16384) {
+    if (!blocksync && DR <= 32 && a.n_items <= 16384 && !a.bin_order) {
         const size_t smem = 128 + (size_t)(SCAN_THREADS / 32) * 2 * (DR + 1) * REG_TILE_N * sizeof(float);
         static int per_sm_w = 0;
         if (per_sm_w == 0) {
@@ -1796,6 +1844,8 @@ int unb_live_build(unb_ctx *ctx, LiveTiles &L, const double *rows_dev, size_t n,
 {
     L.valid = false;
     L.t32_valid = false;
+    L.cluster_valid = false;
+    L.t32_clustered = false;
     L.n = n;
     L.d = d;
     L.dr = (d + 3) / 4 * 4;
@@ -1882,17 +1932,38 @@ int unb_live_prepare32(unb_ctx *ctx, LiveTiles &L, double r2, bool *usable, cuda
     // compared with the radius (otherwise the fp64 filter is the better tool)
     if (!(r2 >= 1e-30 && r2 <= 1e30 && L.namax_host <= 1e30)) return UNB_OK;
     if (!(k32 * (2.0 * L.namax_host + r2) <= r2 / 16.0)) return UNB_OK;
-    if (!L.t32_valid || L.t32_r2 != r2) {
-        const size_t ntiles32 = (L.n + REG_TILE_N - 1) / REG_TILE_N;
+    const size_t ntiles32 = (L.n + REG_TILE_N - 1) / REG_TILE_N;
+    // clustered tile order (unb_cluster.cu): computed once per (re)built block when a large launch
+    // asks for it, kept across in-place row updates (a permutation stays a permutation)
+    const bool can_cluster = L.dr <= 32 && ntiles32 >= 4 && ntiles32 <= unb_cluster_max_tiles();
+    if (L.want_cluster && !L.cluster_valid && can_cluster) {
+        const size_t K = ntiles32;
+        UNB_TRY(unb_reserve(ctx, L.perm32, ntiles32 * REG_TILE_N * sizeof(int)));
+        UNB_TRY(unb_reserve(ctx, L.cl_scratch_i, (3 * L.n + 4 * K + 8) * sizeof(int)));
+        UNB_TRY(unb_reserve(ctx, L.cl_scratch_f, 2 * K * L.d * sizeof(float)));
+        UNB_TRY(unb_reserve(ctx, L.ctiles32, ((K + REG_TILE_N - 1) / REG_TILE_N) * (L.dr + 1) * REG_TILE_N * sizeof(float)));
+        UNB_TRY(unb_launch_cluster_live(ctx, (const double *)L.rows.p, (int)L.n, (int)L.d, (int)K,
+                                        (int *)L.perm32.p, (int *)L.cl_scratch_i.p,
+                                        (float *)L.cl_scratch_f.p, s));
+        L.cluster_valid = true;
+    }
+    const bool clustered = L.cluster_valid && can_cluster;
+    if (!L.t32_valid || L.t32_r2 != r2 || L.t32_clustered != clustered) {
         const size_t slots = ntiles32 * REG_TILE_N;
         UNB_TRY(unb_reserve(ctx, L.tiles32, ntiles32 * (L.dr + 1) * REG_TILE_N * sizeof(float)));
         k_live_build32<<<(unsigned)((slots + 127) / 128), 128, 0, s>>>(
-            (const double *)L.rows.p, (const double *)L.norms.p, (int)L.n, (int)L.d, (int)L.dr,
+            (const double *)L.rows.p, (const double *)L.norms.p,
+            clustered ? (const int *)L.perm32.p : nullptr, (int)L.n, (int)L.d, (int)L.dr,
             (int)ntiles32, r2, k32, (float *)L.tiles32.p);
         ctx->launches++;
         UNB_CUDA(ctx, cudaGetLastError());
+        if (clustered)   // tile centroids follow the rows (in-place row updates move them a little)
+            UNB_TRY(unb_launch_tile_centroids(ctx, (const double *)L.rows.p, (const int *)L.perm32.p,
+                                              (int)L.n, (int)L.d, (int)L.dr, (int)ntiles32,
+                                              (float *)L.ctiles32.p, s));
         L.t32_valid = true;
         L.t32_r2 = r2;
+        L.t32_clustered = clustered;
     }
     *usable = true;
     return UNB_OK;
