@@ -71,7 +71,8 @@ def main():
         report["cases"].append({"case": name, "r2": single[0], "f": single[1],
                                 "collective_us": coll_us, "inside_accept": float(full.mean())})
     report["status"] = "ok"
-    print(json.dumps(report), flush=True)
+    sys.stdout.write("\n" + json.dumps(report) + "\n")
+    sys.stdout.flush()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -45,7 +45,15 @@ def test_nccl_sharded_rebuild_and_inside(world):
     with open(os.path.join(out_dir, "nccl_worker_world%d.log" % world), "w") as f:
         f.write(res.stdout + "\n--- stderr ---\n" + res.stderr[-4000:])
     assert res.returncode == 0, res.stderr[-3000:]
-    reports = [json.loads(line) for line in res.stdout.splitlines() if line.startswith("{")]
+    # the ranks share one stdout: lines can arrive glued together, so scan for objects
+    reports, dec, text, pos = [], json.JSONDecoder(), res.stdout, 0
+    while True:
+        pos = text.find('{"rank"', pos)
+        if pos < 0:
+            break
+        obj, end = dec.raw_decode(text, pos)
+        reports.append(obj)
+        pos = end
     assert sorted(r["rank"] for r in reports) == list(range(world))
     assert all(r["status"] == "ok" and len(r["cases"]) == 3 for r in reports)
     # identical results on all ranks
