@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIBPATH = os.path.join(LIBDIR, "libultranest_b200.so")
-SOURCES = ["unb_api.cu", "unb_region.cu", "unb_scan.cu", "unb_stepfuncs.cu", "unb_sample.cu", "unb_cluster.cu"]
+SOURCES = ["unb_api.cu", "unb_region.cu", "unb_scan.cu", "unb_stepfuncs.cu", "unb_sample.cu", "unb_cluster.cu", "unb_live.cu"]
 HEADERS = ["unb_internal.cuh", "unb_loglike.cuh", os.path.join("..", "..", "include", "ultranest_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]

@@ -67,6 +67,16 @@ int unb_reserve_pinned(unb_ctx *ctx, PinBuf &b, size_t bytes)
     return UNB_OK;
 }
 
+// pin_small may still be read by an asynchronous copy of an earlier call (row patches of the mirror)
+int unb_wait_small(unb_ctx *ctx)
+{
+    if (ctx->ev_small_pending) {
+        UNB_CUDA(ctx, cudaEventSynchronize(ctx->ev_small));
+        ctx->ev_small_pending = false;
+    }
+    return UNB_OK;
+}
+
 namespace {
 
 void free_dev(DevBuf &b)
@@ -354,6 +364,7 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
     free_dev(ctx->boot_idx); free_dev(ctx->boot_meta); free_dev(ctx->boot_out);
     free_dev(ctx->boot_ell);
     free_pin(ctx->pin_small);
+    if (ctx->ev_small) cudaEventDestroy(ctx->ev_small);
     free_dev(ctx->smp_axes); free_dev(ctx->smp_center);
     for (DevBuf &b : ctx->sf) free_dev(b);
     free_dev(ctx->sf_params);
@@ -730,7 +741,11 @@ extern "C" int unb_region_sync_live(unb_ctx *ctx, const double *unormed, size_t 
         return UNB_OK;
     }
     if (!changed.empty()) {
+        // Everything below is stream-ordered on lane 0; nothing waits for the device: the pinned
+        // staging block is guarded by an event (waited for by its next writer), and the host's
+        // bound of the largest squared norm follows the patched rows without a read-back.
         UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+        UNB_TRY(unb_wait_small(ctx));
         const size_t k = changed.size();
         UNB_TRY(unb_reserve_pinned(ctx, ctx->pin_small, k * (rowb + sizeof(int))));
         char *stage = (char *)ctx->pin_small.p;
@@ -740,12 +755,15 @@ extern "C" int unb_region_sync_live(unb_ctx *ctx, const double *unormed, size_t 
             memcpy(stage + r * rowb, unormed + i * ndim, rowb);
             memcpy(R.snapshot.data() + i * ndim, unormed + i * ndim, rowb);
             idx_stage[r] = changed[r];
+            unb_live_note_host_row(R.live, unormed + i * ndim);
             UNB_TRY(h2d(ctx, (char *)R.live.rows.p + i * rowb, stage + r * rowb, rowb, s));
         }
         UNB_TRY(unb_reserve(ctx, ctx->aux3, k * sizeof(int)));
         UNB_TRY(h2d(ctx, ctx->aux3.p, idx_stage, k * sizeof(int), s));
         UNB_TRY(unb_live_update_rows(ctx, R.live, (const int *)ctx->aux3.p, k, s));
-        UNB_CUDA(ctx, cudaStreamSynchronize(s));
+        if (!ctx->ev_small) UNB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_small, cudaEventDisableTiming));
+        UNB_CUDA(ctx, cudaEventRecord(ctx->ev_small, s));
+        ctx->ev_small_pending = true;
     }
     if (rows_changed) *rows_changed = (int64_t)changed.size();
     return UNB_OK;
@@ -793,10 +811,22 @@ extern "C" int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, cons
     RegionState &R = ctx->region;
     cudaStream_t s = S0(ctx);
     R.enlarge = enlarge;
-    if (R.have_ellipsoid && R.ell_d == ndim && R.ell_center_h.size() == ndim &&
-        memcmp(R.ell_center_h.data(), center, ndim * sizeof(double)) == 0 &&
-        memcmp(R.ell_invcov_h.data(), invcov, ndim * ndim * sizeof(double)) == 0)
-        return UNB_OK;   // unchanged since the last call
+    const bool same_shape = R.have_ellipsoid && R.ell_d == ndim && R.ell_center_h.size() == ndim &&
+                            R.ell_invcov_h.size() == ndim * ndim;
+    const bool same_invcov = same_shape && memcmp(R.ell_invcov_h.data(), invcov, ndim * ndim * sizeof(double)) == 0;
+    const bool same_center = same_shape && memcmp(R.ell_center_h.data(), center, ndim * sizeof(double)) == 0;
+    if (same_invcov && same_center) return UNB_OK;   // unchanged since the last call
+    if (same_invcov) {
+        // only the centre moved (every iteration of a run, integrator.py:2756): refresh the device
+        // copy in stream order -- no matrix upload, no constant-bank update, no synchronisation of
+        // this stream (the register prep kernel takes the centre as a kernel argument)
+        UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));
+        R.ell_center_h.assign(center, center + ndim);
+        UNB_TRY(h2d(ctx, R.ell_center.p, R.ell_center_h.data(), ndim * sizeof(double), s));
+        // kernels that read the centre from device memory (d > 32) may run on a caller's stream
+        if (ndim > 32) UNB_CUDA(ctx, cudaStreamSynchronize(s));
+        return UNB_OK;
+    }
     R.ell_center_h.assign(center, center + ndim);
     R.ell_invcov_h.assign(invcov, invcov + ndim * ndim);
     {
@@ -857,6 +887,7 @@ int enqueue_ellipsoid(unb_ctx *ctx, cudaStream_t s, const double *pts_dev, size_
     p.m = (long long)m;
     p.d = (int)d;
     p.center = (const double *)R.ell_center.p;
+    if (d <= 32) memcpy(p.center_arg, R.ell_center_h.data(), d * sizeof(double));
     p.invcov = (const double *)R.ell_invcov.p;
     p.r2 = R.enlarge;
     p.mask = mask_dev;
@@ -901,6 +932,7 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     p.m = (long long)m;
     p.d = (int)d;
     p.center = use_ellipsoid ? (const double *)R.ell_center.p : nullptr;
+    if (d <= 32 && R.ell_center_h.size() == d) memcpy(p.center_arg, R.ell_center_h.data(), d * sizeof(double));
     p.invcov = (const double *)R.ell_invcov.p;
     p.r2 = R.enlarge;
     p.mask = mask_dev;
@@ -1695,9 +1727,10 @@ int bootstrap_enqueue(unb_ctx *ctx, const double *unormed, const double *u, size
     if (want_f) {
         UNB_TRY(unb_reserve(ctx, ctx->boot_u, n * d * sizeof(double)));
         UNB_TRY(h2d(ctx, ctx->boot_u.p, u, n * d * sizeof(double), s));
-        UNB_TRY(unb_reserve_pinned(ctx, ctx->pin_small, (size_t)R * (d + d * d) * sizeof(double)));
         // the pinned block may still be read by an earlier call's copy on another stream
+        UNB_TRY(unb_wait_small(ctx));
         UNB_CUDA(ctx, cudaStreamSynchronize(s));
+        UNB_TRY(unb_reserve_pinned(ctx, ctx->pin_small, (size_t)R * (d + d * d) * sizeof(double)));
         double *hc = (double *)ctx->pin_small.p;
         double *ha = hc + (size_t)R * d;
         for (int r = 0; r < R; r++) {

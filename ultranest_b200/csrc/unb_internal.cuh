@@ -42,6 +42,7 @@ struct PinBuf {
 };
 int unb_reserve(unb_ctx *ctx, DevBuf &b, size_t bytes);
 int unb_reserve_pinned(unb_ctx *ctx, PinBuf &b, size_t bytes);
+int unb_wait_small(unb_ctx *ctx);   // before (re)using ctx->pin_small
 
 // ---------------------------------------------------------------------------------------
 // tiled live block
@@ -197,6 +198,8 @@ struct unb_ctx {
     // bootstrap scratch
     DevBuf boot_rows, boot_u, boot_tiles, boot_idx, boot_meta, boot_out, boot_ell;
     PinBuf pin_small;
+    cudaEvent_t ev_small = nullptr;   // last asynchronous read of pin_small (row patches of the mirror)
+    bool ev_small_pending = false;
     // device-side proposal generation (unb_sample.cu)
     DevBuf smp_axes, smp_center;
     std::vector<double> smp_axes_h;
@@ -217,6 +220,7 @@ int unb_live_build(unb_ctx *ctx, LiveTiles &L, const double *rows_dev, size_t n,
                    cudaStream_t s);
 int unb_live_update_rows(unb_ctx *ctx, LiveTiles &L, const int *rows_dev_idx, size_t nrows,
                          cudaStream_t s);
+void unb_live_note_host_row(LiveTiles &L, const double *row);
 int unb_live_set_h(unb_ctx *ctx, LiveTiles &L, int h_mode, double r2, cudaStream_t s);
 // builds / refreshes the fp32 tiles for radius r2; *usable says whether the fp32 pre-filter is
 // safe and worthwhile for this block and radius (ranges, slack thin compared with r2)
@@ -237,6 +241,9 @@ struct PrepArgs {
     long long m;
     int d;
     const double *center;     // ellipsoid (NULL: every row passes)
+    double center_arg[32];    // register kernel (d <= 32): the centre travels as a kernel argument --
+                              // the integrator moves it every iteration (integrator.py:2756), and a
+                              // kernel argument needs neither an upload nor a stream synchronisation
     const double *invcov;
     double r2;
     unsigned char *mask;      // out: ellipsoid mask (1 byte per row); NULL to skip
@@ -293,6 +300,20 @@ int unb_launch_enlargement_f(unb_ctx *ctx, const double *u, int d, const int *it
 int unb_launch_pairdist(unb_ctx *ctx, const double *pts, const long long *ids, int n, int d,
                         double *partial_sum, long long *partial_cnt, cudaStream_t s);
 size_t unb_max_rowwise_d();
+// one-launch in-place row update of every image of the live block (unb_live.cu)
+struct LiveUpdateArgs {
+    const double *rows;       // row-major fp64 rows (already patched)
+    const int *idx;           // rows to refresh
+    int nrows, n, d, dr, tile_n;
+    double *tiles;            // fp64 tiles (nullable)
+    double *norms;
+    unsigned long long *namax;   // running UPPER BOUND of the largest squared norm (atomicMax)
+    int h_mode;               // HMODE_* currently stored in the fp64 tiles' h row (HMODE_NONE: skip)
+    double h_r2, kappa;
+    float *tiles32;           // fp32 tiles in row order (nullable)
+    double t32_r2, kappa32;
+};
+int unb_launch_live_update(unb_ctx *ctx, const LiveUpdateArgs &a, cudaStream_t s);
 // clustered live tiles + binned proposals (unb_cluster.cu)
 size_t unb_cluster_max_tiles();
 int unb_launch_cluster_live(unb_ctx *ctx, const double *rows, int n, int d, int K, int *perm,

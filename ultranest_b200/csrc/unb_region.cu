@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(128, prep_min_blocks(DR)) k_prep_reg(const Pre
         if (P.center) {
             double dl[DR];
 #pragma unroll
-            for (int k = 0; k < DR; k++) dl[k] = __dsub_rn(p[k], c_ell_center[k]);
+            for (int k = 0; k < DR; k++) dl[k] = __dsub_rn(p[k], P.center_arg[k]);
             // filter: r_fast = d^T (A d) with fused multiply-adds on the folded matrix
             // (d(d+1)/2 + 2d DFMA instead of the einsum's 3 d^2 non-fused operations).  Both r_fast and the reference's sequential
             // einsum value lie within (d^2+2d+4) u * sum|d_j A_jk d_k| <= tol of d^T A d, with
@@ -810,11 +810,9 @@ int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s)
     if (g_const_owner != ctx) {
         g_img_center.clear(); g_img_invcov.clear(); g_img_shift.clear(); g_img_mat.clear();
     }
+    // (the ellipsoid centre is a kernel argument of k_prep_reg, PrepArgs::center_arg)
     std::vector<double> center, invcov, shift, mat;
-    if (R.have_ellipsoid && R.ell_d == d) {
-        center = padded_image(R.ell_center_h, 1, d, dr);
-        invcov = padded_image(R.ell_invcov_h, d, d, dr);
-    }
+    if (R.have_ellipsoid && R.ell_d == d) invcov = padded_image(R.ell_invcov_h, d, d, dr);
     if (R.layer_kind == UNB_LAYER_AFFINE && R.layer_d == d) {
         shift = padded_image(R.layer_shift_h, 1, d, dr);
         mat = padded_image(R.layer_mat_h, d, d, dr);

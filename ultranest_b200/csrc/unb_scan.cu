@@ -23,6 +23,7 @@
 #include "unb_internal.cuh"
 
 #include <climits>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -1883,19 +1884,39 @@ int unb_live_update_rows(unb_ctx *ctx, LiveTiles &L, const int *rows_dev_idx, si
                          cudaStream_t s)
 {
     if (!nrows || L.ntiles == 0) return UNB_OK;
-    k_live_update_rows<<<(unsigned)((nrows + 127) / 128), 128, 0, s>>>(
-        (const double *)L.rows.p, rows_dev_idx, (int)nrows, (int)L.d, (int)L.dr, (int)L.tile_n,
-        (double *)L.tiles.p, (double *)L.norms.p);
-    ctx->launches++;
-    UNB_CUDA(ctx, cudaGetLastError());
-    UNB_CUDA(ctx, cudaMemsetAsync(L.namax.p, 0, sizeof(unsigned long long), s));
-    k_norm_max<<<8, 256, 0, s>>>((const double *)L.norms.p, (int)L.n,
-                                 (unsigned long long *)L.namax.p);
-    ctx->launches++;
-    UNB_CUDA(ctx, cudaGetLastError());
-    L.h_mode = HMODE_NONE;   // h row of the touched slots is stale
-    L.t32_valid = false;     // and so is the fp32 image
+    // one launch refreshes every image of the touched rows (unb_live.cu); the fp32 image follows in
+    // place unless its tiles are in cluster order (then it is rebuilt through the permutation)
+    const bool keep32 = L.t32_valid && !L.t32_clustered;
+    LiveUpdateArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = (const double *)L.rows.p;
+    a.idx = rows_dev_idx;
+    a.nrows = (int)nrows;
+    a.n = (int)L.n;
+    a.d = (int)L.d;
+    a.dr = (int)L.dr;
+    a.tile_n = (int)L.tile_n;
+    a.tiles = (double *)L.tiles.p;
+    a.norms = (double *)L.norms.p;
+    a.namax = (unsigned long long *)L.namax.p;
+    a.h_mode = L.h_mode;
+    a.h_r2 = L.h_r2;
+    a.kappa = unb_kappa(L.d);
+    a.tiles32 = keep32 ? (float *)L.tiles32.p : nullptr;
+    a.t32_r2 = L.t32_r2;
+    a.kappa32 = unb_kappa32(L.d);
+    UNB_TRY(unb_launch_live_update(ctx, a, s));
+    if (!keep32) L.t32_valid = false;
     return UNB_OK;
+}
+
+// the host's copy of the norm bound follows row updates without a device round trip: same
+// k-sequential FMA chain as the kernels, so the two bounds agree bit for bit
+void unb_live_note_host_row(LiveTiles &L, const double *row)
+{
+    double na = 0.0;
+    for (size_t k = 0; k < L.d; k++) na = std::fma(row[k], row[k], na);
+    if (na > L.namax_host) L.namax_host = na;
 }
 
 int unb_live_set_h(unb_ctx *ctx, LiveTiles &L, int h_mode, double r2, cudaStream_t s)

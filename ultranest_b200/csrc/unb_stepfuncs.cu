@@ -598,6 +598,7 @@ int evolve_chunk(unb_ctx *ctx, EvolveArgs A, int threads, double *currentu, cons
                  o_sl = o_r + al(nb), o_sr = o_sl + al(n), o_like = o_sr + al(n), o_acc = o_like + al(nb),
                  o_succ = o_acc + al(n), total = o_succ + al(n);
     UNB_TRY(unb_reserve(ctx, ctx->sf[0], total));
+    UNB_TRY(unb_wait_small(ctx));
     UNB_TRY(unb_reserve_pinned(ctx, ctx->pin_small, total));
     char *dev = (char *)ctx->sf[0].p, *pin = (char *)ctx->pin_small.p;
     memcpy(pin + o_v, currentv, rb);
@@ -875,6 +876,7 @@ extern "C" int unb_popslice_iterate(unb_ctx *ctx, const double *slice_position, 
     cudaStream_t s = S0(ctx);
     const size_t popsize = ctx->ps_popsize, ndim = ctx->ps_ndim;
     // the draws go through pinned staging so the copy is one asynchronous DMA
+    UNB_TRY(unb_wait_small(ctx));
     UNB_TRY(unb_reserve_pinned(ctx, ctx->pin_small, popsize * sizeof(double)));
     memcpy(ctx->pin_small.p, slice_position, popsize * sizeof(double));
     UNB_TRY(up(ctx, ctx->sf[8], ctx->pin_small.p, popsize * sizeof(double), s));
