@@ -61,6 +61,16 @@ def main():
             full = region.inside(pts)
             got = D.sharded_inside(region, pts)
             assert (got == full).all(), ("sharded_inside", name)
+            # throughput mode with the draws split over the ranks: every rank ends with the same
+            # accepted rows, each rank's block comes from its own counter range and is a member
+            region.device_seed = 77
+            rows = D.sharded_sample_device(region, 40000, method="sample_from_wrapping_ellipsoid")
+            digest = float(rows.sum())
+            same = torch.tensor([digest, -digest], dtype=torch.float64, device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MAX)
+            assert same[0].item() == -same[1].item(), "ranks disagree on the gathered rows"
+            assert len(rows) > 1000 and region.inside(rows).all()
+            assert len(np.unique(rows[:, 0])) == len(rows), "ranks drew overlapping proposals"
             sub = slice(0, 6000)
             want_mask = cport.region_inside(
                 pts[sub], region.unormed, lambda p: cport.transform_affine(p, layer.ctr, layer.T),

@@ -100,7 +100,13 @@ def _worker(rank, world, port, out):
         got = D.allgather_rows(rows[lo:hi], 11)
         mask = (np.arange(11) % 3 == 0)
         gotm = D.allgather_rows(mask[lo:hi], 11)
-        out.put(("gather", rank, bool((got == rows).all() and (gotm == mask).all() and gotm.dtype == bool)))
+        ragged = np.arange((rank + 2) * 3, dtype=np.float64).reshape(rank + 2, 3) + 100 * rank
+        gotr = D.allgather_varrows(ragged)
+        wantr = np.concatenate([np.arange((r + 2) * 3, dtype=np.float64).reshape(r + 2, 3) + 100 * r
+                                for r in range(world)])
+        empty = D.allgather_varrows(np.zeros((0, 3)) if rank == 0 else ragged)
+        out.put(("gather", rank, bool((got == rows).all() and (gotm == mask).all() and gotm.dtype == bool
+                                      and (gotr == wantr).all() and len(empty) == 3)))
     finally:
         D.disable()
         dist.destroy_process_group()

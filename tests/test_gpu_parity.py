@@ -350,3 +350,35 @@ def test_membership_fp32_prefilter_agrees_and_edges(eng):
     eng.region_sync_live(a)
     eng.region_set_radius(1e-9)
     assert (eng.region_has_neighbour(a[:500] + 1e-6) == (cport.find_nearby(a, a[:500] + 1e-6, 1e-9) >= 0)).all()
+
+
+@pytest.mark.parametrize("na,nb,d", [(4000, 20000, 20), (3000, 9000, 5), (1200, 6000, 50), (700, 5000, 100)])
+def test_find_nearby_two_phase_bitexact(eng, na, nb, d):
+    """Launches of >= 4096 candidates take the two-phase path (membership kernel first, ordered
+    first-index scan over the members only): indices must be the ordered exact kernel's, in the
+    accepting, mixed and full-scan regimes, and the `<=` edge must survive both phases."""
+    from ultranest_b200 import _native
+    rng = np.random.RandomState(na + nb + d)
+    a = _live(rng, na, d)
+    b = _live(rng, nb, d, scale=1.15)
+    for frac in (0.0, 0.3, 0.97):
+        r2 = _radius_for(a, b, frac) if frac > 0 else 1e-6
+        want = cport.find_nearby(a, b, r2)
+        got = eng.find_nearby(a, b, r2)
+        assert (got == want).all(), (na, nb, d, frac, np.flatnonzero(got != want)[:5])
+    # the edge: radius = an exactly computed pair distance (hit) and the next double below (miss)
+    j, i = 17, int(cport.find_nearby(a, b[17:18], 1e9)[0])
+    D = 0.0
+    for k in range(d):
+        diff = a[i, k] - b[j, k]
+        D = D + diff * diff
+    for r2 in (D, np.nextafter(D, 0)):
+        assert (eng.find_nearby(a, b, r2) == cport.find_nearby(a, b, r2)).all()
+    # exact-only mode (plain kernels, no two-phase) agrees
+    r2 = _radius_for(a, b, 0.3)
+    fast = eng.find_nearby(a, b, r2)
+    eng.set_option(_native.OPT_EXACT_ONLY, 1)
+    try:
+        assert (eng.find_nearby(a, b, r2) == fast).all()
+    finally:
+        eng.set_option(_native.OPT_EXACT_ONLY, 0)

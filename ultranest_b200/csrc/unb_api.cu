@@ -231,6 +231,49 @@ int attach_bins(unb_ctx *ctx, Lane &ln, const LiveTiles &L, ScanArgs &a, cudaStr
     return UNB_OK;
 }
 
+// First-neighbour indices in TWO PHASES when the fp32 membership kernel is available
+// (find_nearby, mlfriends.pyx:143-183): (1) the any-neighbour kernel marks the candidates that have
+// a neighbour at all -- every other candidate is finished with -1 and never enters the ordered
+// scan; (2) the ordered first-index kernel runs over the members only.  In the full-scan regime
+// (no neighbours) FIND then costs what the membership test costs (3.8 instead of 6.5 ms per 2^20
+// candidates at d = 20, 3.6 instead of 10.8 ms per 2^17 at d = 100); with neighbours everywhere
+// it pays the membership pass on top (+12 %).  Indices are those of the ordered exact kernel.
+int find_two_phase(unb_ctx *ctx, Lane &ln, ScanArgs a, cudaStream_t s, bool *done)
+{
+    *done = false;
+    if (!a.tiles32 || ctx->exact_only || !a.out_idx || a.item_idx || a.out_row_idx || a.n_items_dev ||
+        a.n_items < 4096 || a.dr > 128)
+        return UNB_OK;
+    const size_t n = (size_t)a.n_items;
+    UNB_TRY(unb_reserve(ctx, ln.mask, n));
+    UNB_TRY(unb_reserve(ctx, ln.items, n * sizeof(int)));
+    UNB_TRY(unb_reserve(ctx, ln.counter, 4 * sizeof(int)));
+    UNB_TRY(unb_reserve(ctx, ln.smp_counts, unb_compact_scratch_ints((long long)n) * sizeof(int)));
+    UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 4 * sizeof(int), s));
+    UNB_CUDA(ctx, cudaMemsetAsync(a.out_idx, 0xff, n * sizeof(long long), s));   // -1 everywhere
+    ScanArgs any = a;
+    any.out_idx = nullptr;
+    unsigned char *user_mask = a.out_mask;
+    any.out_mask = (unsigned char *)ln.mask.p;
+    any.stat_rechecks = nullptr;
+    UNB_TRY(unb_launch_inside_any(ctx, any, (int *)ln.counter.p + 1, s));
+    int *n_members = (int *)ln.counter.p + 2;
+    UNB_TRY(unb_launch_compact_rows(ctx, (const unsigned char *)ln.mask.p, (long long)n, 0, nullptr,
+                                    nullptr, (int *)ln.smp_counts.p, n_members, nullptr, nullptr,
+                                    (int *)ln.items.p, s));
+    if (user_mask)
+        UNB_CUDA(ctx, cudaMemcpyAsync(user_mask, ln.mask.p, n, cudaMemcpyDeviceToDevice, s));
+    ScanArgs ord = a;
+    ord.tiles32 = nullptr;
+    ord.out_mask = nullptr;
+    ord.item_idx = (const int *)ln.items.p;
+    ord.out_row_idx = (const int *)ln.items.p;
+    ord.n_items_dev = n_members;
+    UNB_TRY(unb_launch_scan(ctx, SCAN_FIND, ord, 1, s));
+    *done = true;
+    return UNB_OK;
+}
+
 // a launch of `m` proposals against the region's live block: ask for clustered tiles when large
 void request_cluster(unb_ctx *ctx, LiveTiles &L, size_t m)
 {
@@ -281,7 +324,19 @@ int scan_host(unb_ctx *ctx, LiveTiles &L, int mode, const double *bpts, size_t n
         UNB_CUDA(ctx, cudaMemsetAsync(ctx->aux0.p, 0, sizeof(unsigned long long), s));
         a.out_round_max = (unsigned long long *)ctx->aux0.p;
     }
-    UNB_TRY(unb_launch_scan(ctx, mode, a, 1, s));
+    bool two_phase = false;
+    if (mode == SCAN_FIND) {
+        ScanArgs pre;
+        memset(&pre, 0, sizeof(pre));
+        UNB_TRY(prepare_threshold(ctx, L, r2, s, &pre));   // fp32 image when safe for this radius
+        ScanArgs a2 = a;
+        a2.tiles32 = pre.tiles32;
+        a2.perm32 = pre.perm32;
+        a2.kappa32 = pre.kappa32;
+        a2.namax32 = pre.namax32;
+        UNB_TRY(find_two_phase(ctx, ln, a2, s, &two_phase));
+    }
+    if (!two_phase) UNB_TRY(unb_launch_scan(ctx, mode, a, 1, s));
     if (mode == SCAN_FIND || mode == SCAN_COUNT)
         UNB_TRY(d2h(ctx, out_idx_host, ln.idx.p, nb * sizeof(long long), s));
     else if (mode == SCAN_SUBTRACT)
@@ -1593,9 +1648,19 @@ extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, 
     a.r2 = ctx->region.r2;
     a.out_idx = (long long *)nnearby_dev;
     a.out_mask = mask_dev;
-    if (nnearby_dev) return unb_launch_scan(ctx, SCAN_FIND, a, 1, s);
-    // mask only: the persistent any-neighbour kernel MLFriends.inside uses
     Lane &ln = ctx->lane[0];
+    if (nnearby_dev) {
+        ScanArgs a2 = a;
+        a2.tiles32 = pre.tiles32;
+        a2.perm32 = pre.perm32;
+        a2.kappa32 = pre.kappa32;
+        a2.namax32 = pre.namax32;
+        bool two_phase = false;
+        UNB_TRY(find_two_phase(ctx, ln, a2, s, &two_phase));
+        if (two_phase) return UNB_OK;
+        return unb_launch_scan(ctx, SCAN_FIND, a, 1, s);
+    }
+    // mask only: the persistent any-neighbour kernel MLFriends.inside uses
     UNB_TRY(unb_reserve(ctx, ln.counter, 2 * sizeof(int)));
     UNB_CUDA(ctx, cudaMemsetAsync(ln.counter.p, 0, 2 * sizeof(int), s));
     UNB_TRY(stat_reset(ctx, s));

@@ -333,7 +333,7 @@ int unb_launch_finish_mask(unb_ctx *ctx, unsigned char *mask_dev, const unsigned
 int unb_launch_compact_rows(unb_ctx *ctx, const unsigned char *mask_dev, long long m, int d,
                             const double *rows_dev, const double *like_dev, int *scratch_counts,
                             int *total_dev, double *out_rows_dev, double *out_like_dev,
-                            long long *out_index_dev, cudaStream_t s);
+                            int *out_index_dev, cudaStream_t s);
 size_t unb_compact_scratch_ints(long long m);
 int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, cudaStream_t s);
 int unb_launch_fp32_peak(unb_ctx *ctx, float *scratch, int blocks, int iters, cudaStream_t s);

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) k_scatter_rows(const unsigned char *__res
                                                       const double *__restrict__ like,
                                                       double *__restrict__ out_rows,
                                                       double *__restrict__ out_like,
-                                                      long long *__restrict__ out_index)
+                                                      int *__restrict__ out_index)
 {
     __shared__ int s_dst[COMPACT_ROWS];
     __shared__ int s_warp[8];
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) k_scatter_rows(const unsigned char *__res
         const int dst = s_dst[i];
         if (dst >= 0) {
             if (out_like) out_like[dst] = like[base + i];
-            if (out_index) out_index[dst] = base + i;
+            if (out_index) out_index[dst] = (int)(base + i);
         }
     }
 }
@@ -267,7 +267,7 @@ int unb_launch_finish_mask(unb_ctx *ctx, unsigned char *mask_dev, const unsigned
 int unb_launch_compact_rows(unb_ctx *ctx, const unsigned char *mask_dev, long long m, int d,
                             const double *rows_dev, const double *like_dev, int *scratch_counts,
                             int *total_dev, double *out_rows_dev, double *out_like_dev,
-                            long long *out_index_dev, cudaStream_t s)
+                            int *out_index_dev, cudaStream_t s)
 {
     if (m <= 0) {
         UNB_CUDA(ctx, cudaMemsetAsync(total_dev, 0, sizeof(int), s));

@@ -246,6 +246,47 @@ def reduce_enlargement(u, unormed, selected, minvol=0., compute_rounds=None, mas
     return float(r2), float(f)
 
 
+def allgather_varrows(local):
+    """Concatenate per-rank row blocks of DIFFERENT lengths in rank order (two collectives: the
+    counts, then the rows padded to the longest block).  Every rank gets the same array."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(_group)
+    local = np.ascontiguousarray(local)
+    dev = _device()
+    n_local = torch.tensor([len(local)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=_group)
+    counts = [int(c.item()) for c in counts]
+    longest = max(max(counts), 1)
+    buf = np.zeros((longest,) + local.shape[1:], dtype=local.dtype)
+    buf[:len(local)] = local
+    send = torch.from_numpy(buf).to(dev)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=_group)
+    return np.concatenate([recv[r].cpu().numpy()[:counts[r]] for r in range(world)], axis=0)
+
+
+def sharded_sample_device(region, nsamples, loglike=None, Lmin=None, method=None, seed=None):
+    """Throughput-mode proposals (``MLFriends.sample_device``: drawn on the device, NOT the
+    reference's random stream) with the DRAWS split over the ranks: every rank draws
+    ``nsamples / world`` proposals from its own range of the generator's counter space, filters
+    them on its GPU, and the accepted rows are re-united in rank order -- the reference's MPI mode
+    does the same with its per-rank streams (gather + bcast of the accepted points,
+    integrator.py:1916-1928).  Every rank returns the same ``rows`` (and ``logl``), so the ranks
+    stay replicas of one sampler while the proposal work is divided by the world size."""
+    world, me = world_size(), rank()
+    lo, hi = shard_bounds(int(nsamples), world, me)
+    out = region.sample_device(hi - lo, method=method, seed=seed, loglike=loglike, Lmin=Lmin)
+    rows, like = out if loglike is not None else (out, None)
+    if world == 1:
+        return out
+    rows = allgather_varrows(rows)
+    if like is not None:
+        return rows, allgather_varrows(like)
+    return rows
+
+
 def sharded_inside(region, pts):
     """``region.inside(pts)`` with the rows split over the ranks; every rank gets the full mask."""
     world, me = world_size(), rank()
