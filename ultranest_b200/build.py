@@ -65,7 +65,7 @@ def build(force=False, verbose=False, extra_flags=()):
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
             list(pool.map(lambda cmd: _run(cmd, verbose), jobs))
-    _run([nvcc, "-shared", "-Xcompiler", "-pthread", "-o", LIBPATH] + objects, verbose)
+    _run([nvcc, "-shared", "-Xcompiler", "-pthread", "-o", LIBPATH] + objects + ["-ldl"], verbose)
     return LIBPATH
 
 

@@ -395,6 +395,7 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
     if (!ctx) return UNB_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    unb_prep_forget_ctx(ctx);
     for (int i = 0; i < 2; i++) {
         Lane &ln = ctx->lane[i];
         free_dev(ln.cand); free_dev(ln.tcand); free_dev(ln.items); free_dev(ln.counter);
@@ -558,6 +559,7 @@ extern "C" int unb_ctx_synchronize(unb_ctx *ctx)
 extern "C" int unb_find_nearby(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
                                size_t nb, size_t ndim, double radiussq, int64_t *nnearby)
 {
+    UNB_RANGE("unb_find_nearby");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, na > nb ? na : nb, ndim));
     if (nb == 0) return UNB_OK;
@@ -574,6 +576,7 @@ extern "C" int unb_find_nearby(unb_ctx *ctx, const double *apts, size_t na, cons
 extern "C" int unb_count_nearby(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
                                 size_t nb, size_t ndim, double radiussq, int64_t *nnearby)
 {
+    UNB_RANGE("unb_count_nearby");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, na > nb ? na : nb, ndim));
     if (nb == 0) return UNB_OK;
@@ -590,6 +593,7 @@ extern "C" int unb_count_nearby(unb_ctx *ctx, const double *apts, size_t na, con
 extern "C" int unb_subtract_nearby(unb_ctx *ctx, const double *apts, size_t n, size_t ndim,
                                    double radiussq, double *bpts_out)
 {
+    UNB_RANGE("unb_subtract_nearby");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, n, ndim));
     if (n == 0) return UNB_OK;
@@ -603,6 +607,7 @@ extern "C" int unb_compute_maxradiussq(unb_ctx *ctx, const double *apts, size_t 
                                        const double *bpts, size_t nb, size_t ndim,
                                        double *maxd_out)
 {
+    UNB_RANGE("unb_compute_maxradiussq");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, na > nb ? na : nb, ndim));
     if (!maxd_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
@@ -677,6 +682,7 @@ extern "C" int unb_inside_ellipsoid(unb_ctx *ctx, const double *points, size_t m
                                     const double *center, const double *invcov,
                                     double square_radius, uint8_t *mask)
 {
+    UNB_RANGE("unb_inside_ellipsoid");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, m, ndim));
     if (m == 0) return UNB_OK;
@@ -769,6 +775,7 @@ extern "C" int unb_untransform_affine(unb_ctx *ctx, const double *ww, size_t m, 
 extern "C" int unb_region_sync_live(unb_ctx *ctx, const double *unormed, size_t n, size_t ndim,
                                     int64_t *rows_changed)
 {
+    UNB_RANGE("unb_region_sync_live");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, n, ndim));
     if (!unormed || n == 0) return unb_fail(ctx, UNB_ERR_ARG, "empty live block");
@@ -1160,6 +1167,7 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
 extern "C" int unb_region_inside(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
                                  int64_t *idx_out)
 {
+    UNB_RANGE("unb_region_inside");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, true));
     if (m == 0) return UNB_OK;
@@ -1170,6 +1178,7 @@ extern "C" int unb_region_inside(unb_ctx *ctx, const double *pts, size_t m, uint
 extern "C" int unb_region_inside_ellipsoid(unb_ctx *ctx, const double *pts, size_t m,
                                            uint8_t *mask)
 {
+    UNB_RANGE("unb_region_inside_ellipsoid");
     UNB_TRY(check_ctx(ctx));
     if (!ctx->region.have_ellipsoid) return unb_fail(ctx, UNB_ERR_STATE, "region ellipsoid not set");
     if (m == 0) return UNB_OK;
@@ -1190,6 +1199,7 @@ extern "C" int unb_region_inside_ellipsoid_dev(unb_ctx *ctx, const double *pts_d
 extern "C" int unb_region_friends(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
                                   int64_t *idx_out)
 {
+    UNB_RANGE("unb_region_friends");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, true));
     if (m == 0) return UNB_OK;
@@ -1200,6 +1210,7 @@ extern "C" int unb_region_friends(unb_ctx *ctx, const double *pts, size_t m, uin
 extern "C" int unb_region_inside_loglike(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask,
                                          double *like, int loglike_kind, const double *lparams)
 {
+    UNB_RANGE("unb_region_inside_loglike");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, true));
     if (m == 0) return UNB_OK;
@@ -1213,6 +1224,7 @@ extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t
                                  const unb_refill_desc *desc, uint8_t *flags, double *like,
                                  int64_t *counts)
 {
+    UNB_RANGE("unb_region_refill");
     UNB_TRY(check_ctx(ctx));
     if (!desc || !counts) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     counts[0] = counts[1] = counts[2] = 0;
@@ -1417,6 +1429,7 @@ extern "C" int unb_region_sample_dev(unb_ctx *ctx, const unb_sample_desc *desc, 
                                      double *rows_out_dev, double *like_out_dev, int32_t *n_out_dev,
                                      void *stream)
 {
+    UNB_RANGE("unb_region_sample_dev");
     UNB_TRY(check_ctx(ctx));
     cudaStream_t s = stream ? (cudaStream_t)stream : S0(ctx);
     UNB_TRY(sample_prepare(ctx, desc, nsamples, s));
@@ -1433,6 +1446,7 @@ extern "C" int unb_region_sample_dev(unb_ctx *ctx, const unb_sample_desc *desc, 
 extern "C" int unb_region_sample(unb_ctx *ctx, const unb_sample_desc *desc, size_t nsamples,
                                  double *rows_out, double *like_out, int64_t *n_out, int64_t *counts)
 {
+    UNB_RANGE("unb_region_sample");
     UNB_TRY(check_ctx(ctx));
     if (!n_out) return unb_fail(ctx, UNB_ERR_ARG, "null pointer");
     *n_out = 0;
@@ -1528,6 +1542,7 @@ extern "C" int unb_sample_draw(unb_ctx *ctx, int method, size_t nsamples, size_t
 extern "C" int unb_region_inside_dev(unb_ctx *ctx, const double *pts_dev, size_t m,
                                      uint8_t *mask_dev, void *stream)
 {
+    UNB_RANGE("unb_region_inside_dev");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, true));
     if (m == 0) return UNB_OK;
@@ -1542,6 +1557,7 @@ extern "C" int unb_region_inside_loglike_dev(unb_ctx *ctx, const double *pts_dev
                                              uint8_t *mask_dev, double *like_dev, int loglike_kind,
                                              const double *lparams, void *stream)
 {
+    UNB_RANGE("unb_region_inside_loglike_dev");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, true));
     if (m == 0) return UNB_OK;
@@ -1555,6 +1571,7 @@ extern "C" int unb_region_inside_loglike_dev(unb_ctx *ctx, const double *pts_dev
 
 extern "C" int unb_region_find_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby)
 {
+    UNB_RANGE("unb_region_find_nearby");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, false));
     if (m == 0) return UNB_OK;
@@ -1601,6 +1618,7 @@ int has_neighbour_host(unb_ctx *ctx, LiveTiles &L, const double *tpts, size_t m,
 extern "C" int unb_has_neighbour(unb_ctx *ctx, const double *apts, size_t na, const double *bpts,
                                  size_t nb, size_t ndim, double radiussq, uint8_t *mask)
 {
+    UNB_RANGE("unb_has_neighbour");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, na > nb ? na : nb, ndim));
     if (nb == 0) return UNB_OK;
@@ -1617,6 +1635,7 @@ extern "C" int unb_has_neighbour(unb_ctx *ctx, const double *apts, size_t na, co
 // the any-neighbour kernel instead of the ordered first-index scan
 extern "C" int unb_region_has_neighbour(unb_ctx *ctx, const double *tpts, size_t m, uint8_t *mask)
 {
+    UNB_RANGE("unb_region_has_neighbour");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, false));
     if (m == 0) return UNB_OK;
@@ -1627,6 +1646,7 @@ extern "C" int unb_region_has_neighbour(unb_ctx *ctx, const double *tpts, size_t
 extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, size_t m,
                                           int64_t *nnearby_dev, uint8_t *mask_dev, void *stream)
 {
+    UNB_RANGE("unb_region_find_nearby_dev");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, false));
     if (m == 0) return UNB_OK;
@@ -1672,6 +1692,7 @@ extern "C" int unb_region_find_nearby_dev(unb_ctx *ctx, const double *tpts_dev, 
 
 extern "C" int unb_region_count_nearby(unb_ctx *ctx, const double *tpts, size_t m, int64_t *nnearby)
 {
+    UNB_RANGE("unb_region_count_nearby");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(region_ready(ctx, false));
     if (m == 0) return UNB_OK;
@@ -1850,6 +1871,7 @@ extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const d
                                     size_t round_lo, size_t round_hi, const double *ctrs,
                                     const double *invcovs, double *maxd_out, double *f_out)
 {
+    UNB_RANGE("unb_region_bootstrap");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, n, ndim));
     const bool want_d = unormed && maxd_out;
@@ -1895,6 +1917,7 @@ extern "C" int unb_region_bootstrap_fold_dev(unb_ctx *ctx, const double *unormed
                                              int host_failed, double tag, double *out5_dev,
                                              void *stream)
 {
+    UNB_RANGE("unb_region_bootstrap_fold_dev");
     UNB_TRY(check_ctx(ctx));
     UNB_TRY(check_dims(ctx, n, ndim));
     const bool want_d = unormed != nullptr;

@@ -7,7 +7,17 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/ultranest_b200.h"
+
+// NVTX range around an ABI call (header-only NVTX v3: a no-op unless a tool is attached), so that
+// a timeline of a run shows the region calls by name next to their kernels
+struct UnbRange {
+    explicit UnbRange(const char *name) { nvtxRangePushA(name); }
+    ~UnbRange() { nvtxRangePop(); }
+};
+#define UNB_RANGE(name) UnbRange unb_range_guard__(name)
 
 // ---------------------------------------------------------------------------------------
 // error handling
@@ -267,6 +277,7 @@ struct PrepArgs {
 bool unb_tile_prep_fits(int d);
 int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s);
 size_t unb_const_maxd();
+void unb_prep_forget_ctx(const unb_ctx *ctx);
 int unb_launch_prep(unb_ctx *ctx, const PrepArgs &p, cudaStream_t s);
 // tail of the fused refill (integrator.py:1790-1805): user transform, tregion, likelihood, Lmin
 struct TailArgs {

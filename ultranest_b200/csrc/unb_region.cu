@@ -762,6 +762,7 @@ int unb_launch_fp64_peak(unb_ctx *ctx, double *scratch, int blocks, int iters, c
 
 size_t unb_const_maxd() { return CONST_MAXD; }
 
+
 // the tile prep kernel serves 32 < d as long as its 128-row tile fits shared memory
 bool unb_tile_prep_fits(int d)
 {
@@ -773,6 +774,15 @@ size_t unb_max_rowwise_d() { return ROW_SMEM_BUDGET / sizeof(double) / 32 - 1; }
 // -- __constant__ parameter block of the register prep kernel -------------------------------
 static const unb_ctx *g_const_owner = nullptr;
 static long long g_const_version = -1;
+
+// a destroyed context must not stay the recorded owner of the constant block
+void unb_prep_forget_ctx(const unb_ctx *ctx)
+{
+    if (g_const_owner == ctx) {
+        g_const_owner = nullptr;
+        g_const_version = -1;
+    }
+}
 
 // what the constant block currently holds (zero-padded images), so that a call re-sends only the
 // arrays that changed: the integrator moves the ellipsoid centre every iteration
@@ -826,6 +836,9 @@ int unb_prep_sync_constants(unb_ctx *ctx, cudaStream_t s)
     const bool new_shift = !shift.empty() && !same_image(shift, g_img_shift);
     const bool new_mat = !mat.empty() && !same_image(mat, g_img_mat);
     if (new_center || new_invcov || new_shift || new_mat) {
+        // the constant block is process-global: kernels of ANOTHER context may still read the old
+        // values (the previous owner's streams are not ours to name, so wait for the device)
+        if (g_const_owner != nullptr && g_const_owner != ctx) UNB_CUDA(ctx, cudaDeviceSynchronize());
         // kernels of either lane may still read the old values
         UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[0].stream));
         UNB_CUDA(ctx, cudaStreamSynchronize(ctx->lane[1].stream));

@@ -57,25 +57,6 @@ __global__ void k_live_build(const double *__restrict__ rows, int n, int d, int 
     norms[slot] = (slot < n) ? na : 0.0;
 }
 
-// rewrite selected rows after an in-place mutation of the mirrored block
-__global__ void k_live_update_rows(const double *__restrict__ rows, const int *__restrict__ idx,
-                                   int nrows, int d, int dr, int tile_n,
-                                   double *__restrict__ tiles, double *__restrict__ norms)
-{
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrows) return;
-    int slot = idx[r];
-    int t = slot / tile_n, c = slot - t * tile_n;
-    double *T = tiles + (size_t)t * (dr + 1) * tile_n + c;
-    double na = 0.0;
-    for (int k = 0; k < dr; k++) {
-        double v = (k < d) ? rows[(size_t)slot * d + k] : 0.0;
-        T[(size_t)k * tile_n] = v;
-        na = fma(v, v, na);
-    }
-    norms[slot] = na;
-}
-
 __global__ void k_norm_max(const double *__restrict__ norms, int n, unsigned long long *out)
 {
     double m = 0.0;
