@@ -237,3 +237,46 @@ def test_mirror_rejects_unusable_buffers_before_any_device_call(stub_engine):
     assert sf.within_unit_cube(np.empty((0, 3))).shape == (0,)
     sf.evolve_update(eb, e, 0.0, eb, eb, e.copy(), e.copy(), e.copy(), eb.copy(), eb.copy(), eb.copy())
     sf.step_back(0.0, np.empty((0, 4)), np.empty(0, dtype=np.int64), e.copy())
+
+
+def test_mirror_rejects_mismatched_shapes_and_generations(stub_engine, ref):
+    """the mirrors hand raw pointers to the C ABI, so every per-walker array must agree
+    in length BEFORE the call (the reference's typed memoryviews raise there), and `step_back`
+    must raise IndexError for a generation outside the chain like NumPy does in the reference."""
+    from ultranest_b200 import stepfuncs as sf
+    rs, _ = ref
+    calls = stub_engine.calls
+    n, d = 6, 3
+    f = np.zeros(n)
+    b = np.zeros(n, dtype=bool)
+    with pytest.raises(ValueError):    # current_left one short
+        sf.evolve_update(b, f[:0], 0.0, b, b, f.copy(), np.zeros(n - 1), f.copy(), b.copy(), b.copy(), b.copy())
+    with pytest.raises(ValueError):    # fewer likelihoods than acceptable walkers
+        sf.evolve_update(np.ones(n, dtype=bool), f[:2], 0.0, b, b, f.copy(), f.copy(), f.copy(),
+                         b.copy(), b.copy(), b.copy())
+    with pytest.raises(ValueError):    # allu / proposed_u disagree in ndim
+        sf.update_vectorised_slice_sampler(f, f.copy(), f.copy(), f, np.zeros((n, d)), np.zeros((n, d)),
+                                           np.arange(n, dtype=np.int64), np.zeros(n, dtype=np.int64), 0.0, 1.0,
+                                           np.zeros((n, d + 1)), f.copy(), np.zeros((n, d)), n)
+    with pytest.raises(ValueError):    # allp / proposed_p disagree
+        sf.update_vectorised_slice_sampler(f, f.copy(), f.copy(), f, np.zeros((n, d)), np.zeros((n, d)),
+                                           np.arange(n, dtype=np.int64), np.zeros(n, dtype=np.int64), 0.0, 1.0,
+                                           np.zeros((n, d)), f.copy(), np.zeros((n, d + 2)), n)
+    with pytest.raises(ValueError):    # generation / currentt shorter than the chains
+        sf.step_back(0.0, np.zeros((n, 4)), np.zeros(n - 1, dtype=np.int64), f.copy())
+    # a walker that has to step back from a generation outside its chain: IndexError in both
+    allL = np.full((n, 4), 1.0)
+    allL[2, 1] = -5.0                  # below the threshold -> walker 2 is "problematic"
+    gen = np.array([1, 2, 7, 1, 0, 3], dtype=np.int64)
+    with pytest.raises(IndexError):
+        rs.step_back(0.0, allL.copy(), gen.copy(), f.copy())
+    with pytest.raises(IndexError):
+        sf.step_back(0.0, allL.copy(), gen.copy(), f.copy())
+    assert stub_engine.calls == calls
+    # an out-of-range generation of a walker that does NOT step back is harmless in both
+    allL2 = np.full((n, 4), 1.0)
+    allL2[0, 0] = -5.0
+    for impl in (rs, sf):
+        a, g, t = allL2.copy(), gen.copy(), f.copy()
+        impl.step_back(0.0, a, g, t)
+        assert g[2] == 7
