@@ -67,6 +67,11 @@ extern "C" {
                                         in the last scan call (diagnostic)                */
 #define UNB_STAT_H2D_BYTES 3
 #define UNB_STAT_D2H_BYTES 4
+#define UNB_STAT_UNCERTAIN 6         /* exact membership decisions of the last host-buffer
+                                        unb_region_inside / _friends / _inside_loglike / _refill call
+                                        that lie within the transform tolerance of the radius
+                                        (unb_region_set_transform_tolerance); 0 = every decision is
+                                        the reference's                                          */
 #define UNB_STAT_TILE_VISITS 5       /* warp x tile filter passes of the last
                                         unb_region_find_nearby_dev(mask-only) call (diagnostic) */
 
@@ -168,6 +173,14 @@ int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, const double *i
 
 /* MLFriends.maxradiussq */
 int unb_region_set_radius(unb_ctx *ctx, double maxradiussq);
+/* AffineLayer.transform is np.dot(w - ctr, T) (mlfriends.pyx:743), i.e. OpenBLAS dgemm, whose
+ * summation order no other implementation can reproduce; the fused calls whiten proposals on the
+ * device in a defined order instead, so the two t-rows differ by a few ulp.  `tau` is the caller's
+ * bound on what that can do to a pair distance near the radius.  The filters are built for
+ * radius + tau, decisions compare with the radius, and every exact decision with
+ * |D - radius| <= tau is counted (UNB_STAT_UNCERTAIN) so that the caller can re-decide the call with
+ * the reference's own transform.  0 (default) switches the reporting off. */
+int unb_region_set_transform_tolerance(unb_ctx *ctx, double tau);
 
 /* replaces MLFriends.inside(pts), mlfriends.pyx:1186-1211 (ellipsoid -> transform ->
  * find_nearby >= 0) in one device pipeline.  idx_out (optional, may be NULL) receives the

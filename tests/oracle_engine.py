@@ -85,6 +85,24 @@ class OracleEngine(object):
     def region_set_radius(self, maxradiussq):
         self._r2 = float(maxradiussq)
 
+    # transform tolerance: a CPU model of UNB_STAT_UNCERTAIN (pairs within tau of the radius after
+    # the DEFINED-order transform; the device counts only the ones it evaluates exactly, a subset)
+    _tau = 0.0
+    _uncertain = 0
+
+    def region_set_transform_tolerance(self, tau):
+        self._tau = float(tau)
+
+    def uncertain(self):
+        return self._uncertain
+
+    def _note_uncertain(self, t):
+        self._uncertain = 0
+        if self._tau > 0 and self._layer[0] == _native.LAYER_AFFINE and len(t):
+            for j in range(0, len(t), 512):
+                D = ((t[j:j + 512, None, :] - self._live[None, :, :])**2).sum(axis=2)
+                self._uncertain += int((np.abs(D - self._r2) <= self._tau).any(axis=1).sum())
+
     def region_set_layer(self, kind, shift=None, mat=None, ndim=0):
         self._layer = (kind, None if shift is None else np.array(shift, dtype=float),
                        None if mat is None else np.array(mat, dtype=float))
@@ -107,8 +125,11 @@ class OracleEngine(object):
         if use_ellipsoid:
             mask = cport.inside_ellipsoid(pts, *self._ell)
         idx = np.full(len(pts), -1, dtype=np.int64)
+        self._uncertain = 0
         if mask.any():
-            idx[mask] = cport.find_nearby(self._live, self._xf(pts[mask]), self._r2)
+            t = self._xf(pts[mask])
+            self._note_uncertain(t)
+            idx[mask] = cport.find_nearby(self._live, t, self._r2)
         mask = idx >= 0
         return (mask, idx) if want_index else mask
 
@@ -168,6 +189,7 @@ class OracleEngine(object):
     def region_refill(self, u, region_mode, check_cube, xform, tregion, like_kind, lparams, Lmin):
         """Stage by stage what integrator.py:1773-1805 does, with the oracle's pieces."""
         self.calls += 1
+        self._uncertain = 0
         u = _native.as_f64(u, 2)
         n = len(u)
         if region_mode == 2:

@@ -31,6 +31,7 @@ STAT_RECHECKS = 2
 STAT_H2D_BYTES = 3
 STAT_D2H_BYTES = 4
 STAT_TILE_VISITS = 5
+STAT_UNCERTAIN = 6
 
 LAYER_IDENTITY = 0
 LAYER_SCALING = 1
@@ -81,6 +82,7 @@ SIGNATURES = {
     "unb_region_set_layer": [_int, _c_vp, _c_vp, _sz],
     "unb_region_set_ellipsoid": [_c_vp, _c_vp, _dbl, _sz],
     "unb_region_set_radius": [_dbl],
+    "unb_region_set_transform_tolerance": [_dbl],
     "unb_region_inside": [_c_vp, _sz, _c_vp, _c_vp],
     "unb_region_friends": [_c_vp, _sz, _c_vp, _c_vp],
     "unb_region_inside_ellipsoid": [_c_vp, _sz, _c_vp],
@@ -381,6 +383,14 @@ class Engine(object):
 
     def region_set_radius(self, maxradiussq):
         self.call("unb_region_set_radius", float(maxradiussq))
+
+    def region_set_transform_tolerance(self, tau):
+        self.call("unb_region_set_transform_tolerance", float(tau))
+
+    def uncertain(self):
+        """Exact membership decisions of the last host-buffer region call that lie within the
+        transform tolerance of the radius (0: every decision is the reference's)."""
+        return self.stat(STAT_UNCERTAIN)
 
     def region_inside(self, pts, want_index=False, use_ellipsoid=True):
         p = as_f64(pts, 2)

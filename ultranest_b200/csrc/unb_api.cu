@@ -172,6 +172,52 @@ int stat_fetch(unb_ctx *ctx, cudaStream_t s)
     return UNB_OK;
 }
 
+// The tolerance only means something next to the radius it was derived for: it is dropped when the
+// radius changes (unb_region_set_radius) and ignored unless it is tiny against the radius (the
+// certain-neighbour margin of the fp32 filter has 1e-6 r2 of slack to absorb it).
+double eff_tau(const unb_ctx *ctx)
+{
+    const RegionState &R = ctx->region;
+    return (R.have_radius && R.unc_tau > 0.0 && R.unc_tau <= 1e-7 * R.r2) ? R.unc_tau : 0.0;
+}
+
+// counter of uncertain exact decisions (transform tolerance): zeroed before a membership call ...
+int unc_reset(unb_ctx *ctx, cudaStream_t s)
+{
+    // the device counter is monotone (zeroed once); a call's count is the increase it observes,
+    // which saves a memset per call on the latency-critical per-iteration path
+    if (!ctx->unc.p) {
+        UNB_TRY(unb_reserve(ctx, ctx->unc, 2 * sizeof(unsigned int)));
+        UNB_CUDA(ctx, cudaMemsetAsync(ctx->unc.p, 0, 2 * sizeof(unsigned int), s));
+        ctx->unc_seen = 0;
+    }
+    ctx->last_uncertain = 0;
+    return UNB_OK;
+}
+// ... and read back without a synchronisation of its own: every lane copies the (monotone) counter
+// into its pinned slot after its last kernel; the later of the two copies has seen everything, so
+// after the call's final stream synchronisations the larger value is the total
+bool unc_active(const unb_ctx *ctx)
+{
+    return ctx->unc.p && eff_tau(ctx) > 0.0 && ctx->region.layer_kind == UNB_LAYER_AFFINE;
+}
+int unc_copy(unb_ctx *ctx, int lane)
+{
+    if (!unc_active(ctx)) return UNB_OK;
+    Lane &ln = ctx->lane[lane];
+    UNB_TRY(unb_reserve_pinned(ctx, ln.pin_n, 4 * sizeof(int)));
+    return d2h(ctx, (unsigned int *)ln.pin_n.p + 2, ctx->unc.p, sizeof(unsigned int), ln.stream);
+}
+void unc_collect(unb_ctx *ctx, bool lane0, bool lane1)
+{
+    if (!unc_active(ctx)) return;
+    unsigned int v = 0;
+    if (lane0 && ctx->lane[0].pin_n.p) v = std::max(v, ((const unsigned int *)ctx->lane[0].pin_n.p)[2]);
+    if (lane1 && ctx->lane[1].pin_n.p) v = std::max(v, ((const unsigned int *)ctx->lane[1].pin_n.p)[2]);
+    ctx->last_uncertain = (long long)(unsigned int)(v - ctx->unc_seen);
+    ctx->unc_seen = v;
+}
+
 ScanArgs scan_args_for(const LiveTiles &L)
 {
     ScanArgs a;
@@ -194,9 +240,19 @@ double sure_namax(const unb_ctx *ctx, const LiveTiles &L)
     return ctx->sure_level ? L.namax_host : (double)INFINITY;
 }
 
-// threshold-mode h row + (when safe and enabled) the fp32 image used by the membership kernel
-int prepare_threshold(unb_ctx *ctx, LiveTiles &L, double r2, cudaStream_t s, ScanArgs *a)
+// The radius the FILTERS of a live block are built for.  For the region's block it is widened by
+// the transform tolerance (ScanArgs::unc_tau): a pair whose device distance is within that
+// tolerance ABOVE the radius must still reach the exact decision, where it is reported as
+// uncertain.  Decisions themselves always compare with the true radius.
+double filter_r2(const unb_ctx *ctx, const LiveTiles &L, double r2)
 {
+    return (&L == &ctx->region.live && r2 == ctx->region.r2) ? r2 + eff_tau(ctx) : r2;
+}
+
+// threshold-mode h row + (when safe and enabled) the fp32 image used by the membership kernel
+int prepare_threshold(unb_ctx *ctx, LiveTiles &L, double r2_true, cudaStream_t s, ScanArgs *a)
+{
+    const double r2 = filter_r2(ctx, L, r2_true);
     UNB_TRY(unb_live_set_h(ctx, L, HMODE_THRESH, r2, s));
     bool ok32 = false;
     UNB_TRY(unb_live_prepare32(ctx, L, r2, &ok32, s));
@@ -304,7 +360,7 @@ int scan_host(unb_ctx *ctx, LiveTiles &L, int mode, const double *bpts, size_t n
     Lane &ln = ctx->lane[0];
     cudaStream_t s = ln.stream;
     const size_t d = L.d;
-    UNB_TRY(unb_live_set_h(ctx, L, mode == SCAN_MIN ? HMODE_MIN : HMODE_THRESH, r2, s));
+    UNB_TRY(unb_live_set_h(ctx, L, mode == SCAN_MIN ? HMODE_MIN : HMODE_THRESH, filter_r2(ctx, L, r2), s));
     UNB_TRY(unb_reserve(ctx, ln.cand, nb * d * sizeof(double)));
     UNB_TRY(h2d(ctx, ln.cand.p, bpts, nb * d * sizeof(double), s));
     UNB_TRY(stat_reset(ctx, s));
@@ -415,7 +471,7 @@ extern "C" int unb_ctx_destroy(unb_ctx *ctx)
     free_dev(ctx->region.ell_center); free_dev(ctx->region.ell_invcov);
     free_dev(ctx->region.ell_invcov_pad); free_dev(ctx->region.layer_mat_pad);
     free_dev(ctx->aux0); free_dev(ctx->aux1); free_dev(ctx->aux2); free_dev(ctx->aux3);
-    free_dev(ctx->stat); free_dev(ctx->lparams); free_dev(ctx->refill_params);
+    free_dev(ctx->stat); free_dev(ctx->unc); free_dev(ctx->lparams); free_dev(ctx->refill_params);
     free_dev(ctx->boot_rows); free_dev(ctx->boot_u); free_dev(ctx->boot_tiles);
     free_dev(ctx->boot_idx); free_dev(ctx->boot_meta); free_dev(ctx->boot_out);
     free_dev(ctx->boot_ell);
@@ -456,6 +512,7 @@ extern "C" int unb_ctx_get_stat(unb_ctx *ctx, int stat, int64_t *value)
     case UNB_STAT_RECHECKS: *value = ctx->last_rechecks; return UNB_OK;
     case UNB_STAT_H2D_BYTES: *value = ctx->h2d_bytes; return UNB_OK;
     case UNB_STAT_D2H_BYTES: *value = ctx->d2h_bytes; return UNB_OK;
+    case UNB_STAT_UNCERTAIN: *value = ctx->last_uncertain; return UNB_OK;
     case UNB_STAT_TILE_VISITS: {
         // refresh from the device counter (written by the any-neighbour kernel)
         unsigned long long v[2] = {0, 0};
@@ -910,9 +967,19 @@ extern "C" int unb_region_set_ellipsoid(unb_ctx *ctx, const double *center, cons
     return UNB_OK;
 }
 
+extern "C" int unb_region_set_transform_tolerance(unb_ctx *ctx, double tau)
+{
+    UNB_TRY(check_ctx(ctx));
+    if (!(tau >= 0.0) || !std::isfinite(tau)) return unb_fail(ctx, UNB_ERR_ARG, "tolerance must be finite and >= 0");
+    ctx->region.unc_tau = tau;
+    return UNB_OK;
+}
+
 extern "C" int unb_region_set_radius(unb_ctx *ctx, double maxradiussq)
 {
     if (!ctx) return UNB_ERR_ARG;
+    if (!ctx->region.have_radius || ctx->region.r2 != maxradiussq)
+        ctx->region.unc_tau = 0.0;   // a transform tolerance belongs to the radius it was derived for
     ctx->region.r2 = maxradiussq;
     ctx->region.have_radius = true;
     return UNB_OK;
@@ -978,7 +1045,7 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     // mask-only requests on a tiled live block go through the register prep kernel (constant
     // memory parameters, fused likelihood) and the persistent any-neighbour kernel
     // (d <= 32: register prep kernel; 32 < d <= 128: generic prep kernel + fp32 membership kernel)
-    const bool have32 = R.live.t32_valid && R.live.t32_r2 == R.r2 && ctx->filter_fp32;
+    const bool have32 = R.live.t32_valid && R.live.t32_r2 == filter_r2(ctx, R.live, R.r2) && ctx->filter_fp32;
     const bool reg_prep = !ctx->exact_only && !idx_dev && R.live.ntiles > 0 && R.live.dr <= 32;
     const bool use_any = reg_prep || (!ctx->exact_only && !idx_dev && have32);
     // 32 < d: tile prep kernel (register-blocked products out of shared memory)
@@ -1025,6 +1092,12 @@ int enqueue_inside(unb_ctx *ctx, Lane &ln, cudaStream_t s, const double *pts_dev
     a.r2 = R.r2;
     a.out_mask = mask_dev;
     a.out_idx = idx_dev;
+    if (use_any && R.layer_kind == UNB_LAYER_AFFINE && eff_tau(ctx) > 0.0 && ctx->unc.p) {
+        // proposals were whitened on the device in the defined order: report exact decisions that
+        // the reference's np.dot transform could turn around (the shim re-decides such calls)
+        a.unc_tau = eff_tau(ctx);
+        a.unc_count = (unsigned int *)ctx->unc.p;
+    }
     if (use_any) {
         a.out_like = fuse_like ? like_dev : nullptr;
         if (have32) {
@@ -1085,6 +1158,7 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
     if (!ellipsoid_only) {
         request_cluster(ctx, R.live, chunk);
         UNB_TRY(prepare_threshold(ctx, R.live, R.r2, S0(ctx), nullptr));
+        UNB_TRY(unc_reset(ctx, S0(ctx)));
     }
     UNB_CUDA(ctx, cudaStreamSynchronize(S0(ctx)));
     const bool src_pinned = host_is_pinned(pts);
@@ -1151,6 +1225,10 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
         };
         rc = body();
     }
+    if (rc == UNB_OK && !ellipsoid_only) {
+        rc = unc_copy(ctx, 0);
+        if (rc == UNB_OK && c > 1) rc = unc_copy(ctx, 1);
+    }
     for (int i = 0; i < 2; i++) {
         cudaStreamSynchronize(ctx->lane[i].stream);
         lane_flush(ctx->lane[i]);
@@ -1158,6 +1236,7 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
     if (rc == UNB_OK) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return unb_fail(ctx, UNB_ERR_CUDA, "inside pipeline: %s", cudaGetErrorString(e));
+        if (!ellipsoid_only) unc_collect(ctx, true, c > 1);
     }
     return rc;
 }
@@ -1272,6 +1351,7 @@ extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t
     if (desc->region_mode != 0) {
         request_cluster(ctx, R.live, chunk);
         UNB_TRY(prepare_threshold(ctx, R.live, R.r2, s0, nullptr));
+        UNB_TRY(unc_reset(ctx, s0));
     }
     UNB_CUDA(ctx, cudaStreamSynchronize(s0));
 
@@ -1344,11 +1424,16 @@ extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t
         };
         rc = body();
     }
+    if (rc == UNB_OK && desc->region_mode != 0) {
+        rc = unc_copy(ctx, 0);
+        if (rc == UNB_OK && c > 1) rc = unc_copy(ctx, 1);
+    }
     for (int i = 0; i < 2; i++) {
         cudaStreamSynchronize(ctx->lane[i].stream);
         lane_flush(ctx->lane[i]);
     }
     if (rc != UNB_OK) return rc;
+    if (desc->region_mode != 0) unc_collect(ctx, true, c > 1);
     int cnt_host[4] = {0, 0, 0, 0};
     UNB_TRY(d2h(ctx, cnt_host, cnt_dev, 3 * sizeof(int), s0));
     UNB_CUDA(ctx, cudaStreamSynchronize(s0));

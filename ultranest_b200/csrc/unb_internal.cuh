@@ -140,6 +140,13 @@ struct ScanArgs {
     double *out_min;          // MIN: per-candidate exact min distance        (nullable)
     double *out_like;         // any-kernel: rows without a neighbour get -inf (nullable)
     unsigned long long *out_round_max;   // MIN: per-round max over candidates (ordered bits)
+    // Transform tolerance (membership kernels): the device whitens proposals in a DEFINED order,
+    // the reference with OpenBLAS dgemm; the two t-rows differ by a few ulp, so a pair distance
+    // within unc_tau of the radius could be decided differently by the reference.  Such exact
+    // decisions are counted here, and the host shim re-decides the call with the reference's own
+    // np.dot transform (never observed in 4e7 proposals; ~1e-12 relative wide).  0 / NULL: off.
+    double unc_tau;
+    unsigned int *unc_count;
     unsigned long long *stat_rechecks;   // diagnostic counter (nullable)
     unsigned long long *stat_tiles;      // diagnostic: warp-tiles filtered (nullable)
 };
@@ -163,6 +170,7 @@ struct RegionState {
     size_t pad_stride = 0;
     bool have_radius = false;
     double r2 = 0.0;
+    double unc_tau = 0.0;          // transform tolerance on pair distances (0: not reported)
     long long param_version = 0;   // bumped whenever layer / ellipsoid parameters change
 };
 
@@ -203,6 +211,9 @@ struct unb_ctx {
     RegionState region;
     LiveTiles scratch_live;          // stateless calls
     DevBuf aux0, aux1, aux2, aux3, stat;
+    DevBuf unc;                      // one uint: exact decisions inside the transform tolerance
+    long long last_uncertain = 0;    // ... of the last host-buffer membership call
+    unsigned int unc_seen = 0;       // value of the (monotone) device counter at the last read
     DevBuf lparams;                  // likelihood parameters
     DevBuf refill_params;            // fused refill: xform scale/lo, tregion center/invcov, counters
     // bootstrap scratch
@@ -461,6 +472,12 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
     rc = *reinterpret_cast<unsigned long long *>(&c);
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2 *>(&rd);
+}
+
+// an exact membership decision that the reference could take differently (see ScanArgs::unc_tau)
+__device__ __forceinline__ void unc_note(const ScanArgs &A, double D)
+{
+    if (A.unc_count != nullptr && fabs(__dsub_rn(D, A.r2)) <= A.unc_tau) atomicAdd(A.unc_count, 1u);
 }
 
 #endif  // __CUDACC__

@@ -549,6 +549,7 @@ k_inside_any(const ScanArgs A, int *__restrict__ queue_head)
                         pend[m] &= pend[m] - 1ull;
                         rechecks++;
                         const double D = exact_dist_reg<DR>(a[m], T + col);
+                        unc_note(A, D);
                         if (D <= A.r2) {
                             hit[m] = 1;
                             thrkey[m] = INT_MAX;
@@ -926,6 +927,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
 #pragma unroll
                             for (int j = 0; j < 12; j++) D = sq_step(D, lv[j], cv[j]);
                         }
+                        unc_note(A, D);
                         if (D <= A.r2) {
                             hit[m] = 1;
                             thr_lo[m] = __int_as_float(0x7f800000);
@@ -1050,6 +1052,7 @@ k_inside_any32(const ScanArgs A, int *__restrict__ queue_head)
                                     const double *lp = A.live_rows + (size_t)(A.perm32 ? A.perm32[lslot] : lslot) * d;
                                     double D = 0.0;
                                     for (int kk = 0; kk < d; kk++) D = sq_step(D, __ldg(lp + kk), __ldg(cp + kk));
+                                    unc_note(A, D);
                                     ok = D <= A.r2;
                                     rechecks++;
                                 }
@@ -1287,6 +1290,7 @@ k_inside_any32w(const ScanArgs A, int *__restrict__ queue_head)
 #pragma unroll
                         for (int j = 0; j < 12; j++) D = sq_step(D, lv[j], cv[j]);
                     }
+                    unc_note(A, D);
                     if (D <= A.r2) {
                         hit[m] = 1;
                         thr_lo[m] = __int_as_float(0x7f800000);

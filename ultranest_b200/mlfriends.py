@@ -595,7 +595,56 @@ class MLFriends(object):
             kind, shift, mat = layer._device_params(self.u.shape[1])
             eng.region_set_layer(kind, shift, mat, self.u.shape[1])
             eng.region_set_ellipsoid(self.ellipsoid_center, self.ellipsoid_invcov, self.enlarge)
+            eng.region_set_transform_tolerance(self._transform_tolerance())
         return eng
+
+    def _transform_tolerance(self):
+        """Bound ``tau`` on what the layer transform's summation order can do to a pair distance
+        near the radius.  The fused device calls whiten proposals in a defined order, the
+        reference with ``np.dot`` (OpenBLAS); either way a t-coordinate is a d-term sum of
+        products, so the two differ by at most ``delta = 2 (d+2) u |x| |T|_F`` per row
+        (``x = w - ctr``; rows that reach the neighbour scan lie inside the wrapping ellipsoid, so
+        ``|x| <= sqrt(enlarge) * max axis + sqrt(d)``), and a squared distance near ``r^2`` by at
+        most ``2 r delta + delta^2`` plus the rounding of its own sum.  The library reports exact
+        decisions within ``tau`` of the radius; :meth:`inside` then re-decides the call with the
+        reference's own transform.  Zero for layers whose device transform is
+        bit-exact (scaling / identity)."""
+        layer = self.transformLayer
+        if not isinstance(layer, AffineLayer) or not layer._is_learned():
+            return 0.0
+        invcov = self.ellipsoid_invcov      # the matrix the device filter uses (callers may set it)
+        key = (id(layer.T), id(invcov), float(self.enlarge), float(self.maxradiussq))
+        cached = getattr(self, '_tau_cache', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        ndim = self.u.shape[1]
+        eps = 2.0**-53
+        tfro = float(np.sqrt((np.asarray(layer.T, dtype=float)**2).sum()))
+        lam_min = float(np.linalg.eigvalsh(np.asarray(invcov, dtype=float))[0])
+        if not lam_min > 0:
+            return 0.0
+        xmax = (float(self.enlarge) / lam_min)**0.5 + ndim**0.5   # longest semi-axis + |c_ell - ctr|
+        delta = 2.0 * (ndim + 2) * eps * xmax * tfro
+        r2 = float(self.maxradiussq)
+        tau = 2.0 * (2.0 * r2**0.5 * delta + delta * delta + 2.0 * (ndim + 2) * eps * r2)
+        if not np.isfinite(tau):
+            tau = 0.0
+        self._tau_cache = (key, tau)
+        return tau
+
+    def _members_host_transform(self, pts, use_ellipsoid=True, check_cube=False):
+        """Membership decided like the reference does it (mlfriends.pyx:1186-1211): ellipsoid on the
+        device in the einsum order, layer transform with the reference's ``np.dot`` on the HOST,
+        exact neighbour scan on the device.  The fused calls fall back to this when the library
+        reports a decision inside the transform tolerance (one call in many thousands)."""
+        pts = np.asarray(pts, dtype=float)
+        mask = self.inside_ellipsoid(pts) if use_ellipsoid else np.ones(len(pts), dtype=bool)
+        if check_cube:
+            mask &= np.logical_and(pts > 0, pts < 1).all(axis=1)
+        if mask.any():
+            bpts = self.transformLayer.transform(pts[mask, :])
+            mask[mask] = self._bind(need_ellipsoid=False).region_has_neighbour(bpts)
+        return mask
 
     def _fused_ok(self):
         """May proposals be transformed on the device?  Not with circular dimensions (host wrap),
@@ -648,7 +697,10 @@ class MLFriends(object):
         (mlfriends.pyx:1135-1160)."""
         w, wmask = self._draw_in_wrapping_ellipsoid(nsamples)
         if self._fused_ok():     # transform + neighbour scan in one device pipeline
-            vmask = self._bind().region_inside(w[wmask, :], use_ellipsoid=False)
+            eng = self._bind()
+            vmask = eng.region_inside(w[wmask, :], use_ellipsoid=False)
+            if eng.uncertain():
+                vmask = self._members_host_transform(w[wmask, :], use_ellipsoid=False)
         else:
             v = self.transformLayer.transform(w[wmask, :])
             vmask = self._bind(need_ellipsoid=False).region_has_neighbour(v)
@@ -734,13 +786,13 @@ class MLFriends(object):
         first-neighbour scan)."""
         pts = np.asarray(pts, dtype=float)
         if self._fused_ok():
-            return self._bind().region_inside(pts)
-        # circular parameters: wrap on the host like the reference, scans on the device
-        mask = self.inside_ellipsoid(pts)
-        if mask.any():
-            bpts = self.transformLayer.transform(pts[mask, :])
-            mask[mask] = self._bind(need_ellipsoid=False).region_has_neighbour(bpts)
-        return mask
+            eng = self._bind()
+            mask = eng.region_inside(pts)
+            if not eng.uncertain():
+                return mask
+            # a pair distance within the transform tolerance of the radius: decide like the reference
+        # (also: circular parameters are wrapped on the host like the reference, scans on the device)
+        return self._members_host_transform(pts)
 
     def inside_and_loglike(self, pts, loglike):
         """Fused proposal evaluation (integrator.py:1776-1804 without the host
@@ -749,7 +801,16 @@ class MLFriends(object):
         device likelihoods of :mod:`ultranest_b200.likelihoods`."""
         pts = np.asarray(pts, dtype=float)
         kind, lparams = loglike.device_spec(pts.shape[1])
-        return self._bind().region_inside_loglike(pts, kind, lparams)
+        eng = self._bind()
+        mask, like = eng.region_inside_loglike(pts, kind, lparams)
+        if eng.uncertain():   # re-decide with the reference's transform, patch the rows that change
+            ref_mask = self._members_host_transform(pts)
+            gained = ref_mask & ~mask
+            if gained.any():
+                like[gained] = loglike(pts[gained, :])
+            like[~ref_mask] = -np.inf
+            mask = ref_mask
+        return mask, like
 
     def create_ellipsoid(self, minvol=0.0):
         """Wrapping ellipsoid of the live points and its axes (mlfriends.pyx:1213-1237)."""

@@ -88,6 +88,20 @@ def refill_samples(sampler, Lmin, ndraw, nit, loglike=None, transform=None, stat
     else:
         flags, logl_all, (nu, nt, _) = eng.region_refill(rows, region_mode, check_cube, xform,
                                                          treg, kind, lparams, Lmin)
+        if region_mode != 0 and eng.uncertain():
+            # a pair distance within the transform tolerance of the radius (mlfriends.py,
+            # `_transform_tolerance`): membership with the reference's own np.dot transform, then
+            # the same device tail on the members
+            member = region._members_host_transform(rows, use_ellipsoid=(region_mode == 2),
+                                                    check_cube=check_cube)
+            flags = np.zeros(len(rows), dtype=np.uint8)
+            logl_all = np.full(len(rows), -np.inf)
+            nu, nt = int(member.sum()), 0
+            if nu:
+                f2, l2, (_, nt, _) = eng.region_refill(rows[member, :], 0, False, xform, treg, kind,
+                                                       lparams, Lmin)
+                flags[member] = f2 | _native.REFILL_MEMBER
+                logl_all[member] = l2
     if region_mode != 0:
         region._after_sample(nu)
     if stats is not None:
