@@ -1145,6 +1145,33 @@ int upload_lparams(unb_ctx *ctx, int kind, const double *lparams, size_t d, cuda
     return UNB_OK;
 }
 
+// Row counts of the pipeline chunks of a host-buffer call.  The call is bound by the H2D copies
+// (PCIe); what it pays on top is the kernels + D2H of the LAST chunk, which nothing overlaps.  So
+// the chunks are full-sized while there is plenty left and halve towards the end (down to 2^15
+// rows): 3.40 -> 3.25 ms per 2^20 x 20 batch on B200 (tools/chunk_sweep.py).  An explicit
+// UNB_OPT_CHUNK_ROWS gives uniform chunks.
+std::vector<size_t> chunk_plan(const unb_ctx *ctx, size_t m)
+{
+    std::vector<size_t> plan;
+    if (ctx->chunk_rows > 0) {
+        const size_t c = (size_t)ctx->chunk_rows;
+        for (size_t off = 0; off < m; off += c) plan.push_back(std::min(c, m - off));
+        return plan;
+    }
+    const size_t base = (size_t)1 << 18, floor_rows = (size_t)1 << 15;
+    size_t left = m;
+    while (left > base) {
+        plan.push_back(base);
+        left -= base;
+    }
+    while (left > 0) {   // taper
+        size_t c = left > 2 * floor_rows ? (left + 1) / 2 : left;
+        plan.push_back(c);
+        left -= c;
+    }
+    return plan;
+}
+
 // chunked, double-buffered host pipeline: H2D(c+1) overlaps kernels(c) and D2H(c)
 int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_t *idx_out,
                 double *like, int loglike_kind, bool use_ellipsoid = true,
@@ -1153,8 +1180,8 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
     RegionState &R = ctx->region;
     const size_t d = ellipsoid_only ? R.ell_d : R.live.d;
     const size_t rowb = d * sizeof(double);
-    size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18);
-    if (chunk > m) chunk = m;
+    const std::vector<size_t> plan = chunk_plan(ctx, m);
+    const size_t chunk = *std::max_element(plan.begin(), plan.end());   // buffer size per lane
     if (!ellipsoid_only) {
         request_cluster(ctx, R.live, chunk);
         UNB_TRY(prepare_threshold(ctx, R.live, R.r2, S0(ctx), nullptr));
@@ -1167,8 +1194,8 @@ int inside_host(unb_ctx *ctx, const double *pts, size_t m, uint8_t *mask, int64_
     const bool idx_pinned = idx_out ? host_is_pinned(idx_out) : true;
     int rc = UNB_OK;
     size_t c = 0;
-    for (size_t off = 0; off < m && rc == UNB_OK; off += chunk, c++) {
-        const size_t rows = std::min(chunk, m - off);
+    for (size_t off = 0; c < plan.size() && rc == UNB_OK; off += plan[c], c++) {
+        const size_t rows = plan[c];
         Lane &ln = ctx->lane[c & 1];
         cudaStream_t s = ln.stream;
         lane_flush(ln);
@@ -1346,8 +1373,8 @@ extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t
     int *cnt_dev = (int *)(P + nparam);
     UNB_CUDA(ctx, cudaMemsetAsync(cnt_dev, 0, 4 * sizeof(int), s0));
     const size_t rowb = d * sizeof(double);
-    size_t chunk = ctx->chunk_rows > 0 ? (size_t)ctx->chunk_rows : (size_t)(1 << 18);
-    if (chunk > m) chunk = m;
+    const std::vector<size_t> plan = chunk_plan(ctx, m);
+    const size_t chunk = *std::max_element(plan.begin(), plan.end());
     if (desc->region_mode != 0) {
         request_cluster(ctx, R.live, chunk);
         UNB_TRY(prepare_threshold(ctx, R.live, R.r2, s0, nullptr));
@@ -1360,8 +1387,8 @@ extern "C" int unb_region_refill(unb_ctx *ctx, const double *u, size_t m, size_t
     const bool like_pinned = host_is_pinned(like);
     int rc = UNB_OK;
     size_t c = 0;
-    for (size_t off = 0; off < m && rc == UNB_OK; off += chunk, c++) {
-        const size_t rows = std::min(chunk, m - off);
+    for (size_t off = 0; c < plan.size() && rc == UNB_OK; off += plan[c], c++) {
+        const size_t rows = plan[c];
         Lane &ln = ctx->lane[c & 1];
         cudaStream_t s = ln.stream;
         lane_flush(ln);
