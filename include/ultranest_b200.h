@@ -244,6 +244,19 @@ int unb_region_bootstrap_fold_dev(unb_ctx *ctx, const double *unormed, const dou
                                   const double *invcovs, int host_failed, double tag,
                                   double *out5_dev, void *stream);
 
+/* First and second moments of the SELECTED rows of every bootstrap round about the reference point
+ * c0[ndim], accumulated on the device:  sums[r][p] = sum_i y_ip,  sxx[r][p][q] = sum_i y_ip y_iq
+ * (upper triangle q >= p filled), y = u[selected[r]] - c0;  counts[r] = selected rows.  They give the
+ * per-round bounding_ellipsoid (mlfriends.pyx:426-476: mean, np.cov) up to summation order -- good
+ * enough to SCREEN the rounds: MLFriends.compute_enlargement needs only max_r f_r, so only the
+ * rounds whose screened f is within a margin of the maximum are recomputed with the reference's own
+ * NumPy algebra (the result stays bit-identical, the host does 1-2 rounds of np.cov + inv instead of
+ * 30).  Rounds outside [round_lo, round_hi) are left untouched. */
+int unb_region_bootstrap_moments(unb_ctx *ctx, const double *u, size_t n, size_t ndim,
+                                 const uint8_t *selected, size_t nrounds, size_t round_lo,
+                                 size_t round_hi, const double *c0, double *sums, double *sxx,
+                                 int64_t *counts);
+
 /* ---------------------------------------------- vectorised likelihood batch call */
 
 /* Same (params, d, n, like) shape as languages/c/mylib.c:33 my_c_likelihood_vectorized. */

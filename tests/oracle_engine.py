@@ -148,6 +148,22 @@ class OracleEngine(object):
         self.calls += 1
         return cport.count_nearby(self._live, tpts, self._r2)
 
+    def region_bootstrap_moments(self, u, selected, c0, round_lo=0, round_hi=None):
+        """CPU model of unb_region_bootstrap_moments (any summation order will do: it only screens)."""
+        self.calls += 1
+        u = np.asarray(u, dtype=float)
+        selected = np.asarray(selected, dtype=bool)
+        nrounds, d = len(selected), u.shape[1]
+        round_hi = nrounds if round_hi is None else round_hi
+        sums, sxx = np.zeros((nrounds, d)), np.zeros((nrounds, d, d))
+        counts = np.zeros(nrounds, dtype=np.int64)
+        for r in range(round_lo, round_hi):
+            y = u[selected[r]] - c0
+            counts[r] = len(y)
+            sums[r] = y.sum(axis=0)
+            sxx[r] = np.triu(np.dot(y.T, y))
+        return counts, sums, sxx
+
     def region_bootstrap(self, unormed, selected, u=None, ctrs=None, invcovs=None,
                          round_lo=0, round_hi=None):
         self.calls += 1

@@ -94,6 +94,7 @@ SIGNATURES = {
     "unb_region_find_nearby_dev": [_c_vp, _sz, _c_vp, _c_vp, _c_vp],
     "unb_region_bootstrap": [_c_vp, _c_vp, _sz, _sz, _c_vp, _sz, _sz, _sz, _c_vp, _c_vp,
                              _c_vp, _c_vp],
+    "unb_region_bootstrap_moments": [_c_vp, _sz, _sz, _c_vp, _sz, _sz, _sz, _c_vp, _c_vp, _c_vp, _c_vp],
     "unb_region_bootstrap_fold_dev": [_c_vp, _c_vp, _sz, _sz, _c_vp, _sz, _sz, _sz, _c_vp, _c_vp,
                                       _int, _dbl, _c_vp, _c_vp],
     "unb_loglike_gauss": [_c_vp, _sz, _sz, _c_vp, _c_vp, _dbl, _dbl],
@@ -456,6 +457,25 @@ class Engine(object):
                   _ptr(ctrs) if want_f else None, _ptr(invcovs) if want_f else None,
                   _ptr(maxd), _ptr(f))
         return maxd, f
+
+    def region_bootstrap_moments(self, u, selected, c0, round_lo=0, round_hi=None):
+        """Per-round ``(count, sum(y), sum(y y^T))`` of the selected rows about ``c0``
+        (``unb_region_bootstrap_moments``; upper triangle of the second moments filled)."""
+        u = as_f64(u, 2)
+        n, d = u.shape
+        sel = np.ascontiguousarray(selected, dtype=np.uint8)
+        if sel.ndim != 2 or sel.shape[1] != n:
+            raise ValueError("selected must be (nrounds, n)")
+        nrounds = sel.shape[0]
+        if round_hi is None:
+            round_hi = nrounds
+        c0 = as_f64(c0, 1)
+        sums = np.zeros((nrounds, d))
+        sxx = np.zeros((nrounds, d, d))
+        counts = np.zeros(nrounds, dtype=np.int64)
+        self.call("unb_region_bootstrap_moments", _ptr(u), n, d, _ptr(sel), nrounds, int(round_lo),
+                  int(round_hi), _ptr(c0), _ptr(sums), _ptr(sxx), _ptr(counts))
+        return counts, sums, sxx
 
     def region_bootstrap_fold_dev(self, unormed, selected, u, ctrs, invcovs, round_lo, round_hi,
                                   host_failed, tag, out_ptr, stream=None):

@@ -2022,6 +2022,51 @@ extern "C" int unb_region_bootstrap(unb_ctx *ctx, const double *unormed, const d
     return UNB_OK;
 }
 
+extern "C" int unb_region_bootstrap_moments(unb_ctx *ctx, const double *u, size_t n, size_t ndim,
+                                            const uint8_t *selected, size_t nrounds, size_t round_lo,
+                                            size_t round_hi, const double *c0, double *sums, double *sxx,
+                                            int64_t *counts)
+{
+    UNB_RANGE("unb_region_bootstrap_moments");
+    UNB_TRY(check_ctx(ctx));
+    UNB_TRY(check_dims(ctx, n, ndim));
+    if (!u || !selected || !c0 || !sums || !sxx || !counts || n == 0)
+        return unb_fail(ctx, UNB_ERR_ARG, "null pointer / empty live block");
+    if (round_hi > nrounds) round_hi = nrounds;
+    if (round_lo >= round_hi) return UNB_OK;
+    cudaStream_t s = S0(ctx);
+    const size_t d = ndim;
+    const int R = (int)(round_hi - round_lo);
+    std::vector<int> idxA, offA, nA;
+    int maxA = 0;
+    for (size_t r = round_lo; r < round_hi; r++) {
+        const uint8_t *sel = selected + r * n;
+        offA.push_back((int)idxA.size());
+        for (size_t i = 0; i < n; i++)
+            if (sel[i]) idxA.push_back((int)i);
+        nA.push_back((int)idxA.size() - offA.back());
+        counts[r] = nA.back();
+        maxA = std::max(maxA, nA.back());
+    }
+    UNB_TRY(unb_reserve(ctx, ctx->boot_u, n * d * sizeof(double)));
+    UNB_TRY(h2d(ctx, ctx->boot_u.p, u, n * d * sizeof(double), s));
+    UNB_TRY(unb_reserve(ctx, ctx->boot_idx, (idxA.size() + 1) * sizeof(int)));
+    UNB_TRY(h2d(ctx, ctx->boot_idx.p, idxA.data(), idxA.size() * sizeof(int), s));
+    UNB_TRY(unb_reserve(ctx, ctx->boot_meta, 4 * (size_t)R * sizeof(int)));
+    int *dOff = (int *)ctx->boot_meta.p, *dN = dOff + R;
+    UNB_TRY(h2d(ctx, dOff, offA.data(), R * sizeof(int), s));
+    UNB_TRY(h2d(ctx, dN, nA.data(), R * sizeof(int), s));
+    UNB_TRY(unb_reserve(ctx, ctx->boot_ell, ((size_t)R * (d + d * d) + d) * sizeof(double)));
+    double *dSums = (double *)ctx->boot_ell.p, *dSxx = dSums + (size_t)R * d, *dC0 = dSxx + (size_t)R * d * d;
+    UNB_TRY(h2d(ctx, dC0, c0, d * sizeof(double), s));
+    UNB_TRY(unb_launch_round_moments(ctx, (const double *)ctx->boot_u.p, (int)d, (const int *)ctx->boot_idx.p,
+                                     dOff, dN, maxA, R, dC0, dSums, dSxx, s));
+    UNB_TRY(d2h(ctx, sums + round_lo * d, dSums, (size_t)R * d * sizeof(double), s));
+    UNB_TRY(d2h(ctx, sxx + round_lo * d * d, dSxx, (size_t)R * d * d * sizeof(double), s));
+    UNB_CUDA(ctx, cudaStreamSynchronize(s));
+    return UNB_OK;
+}
+
 extern "C" int unb_region_bootstrap_fold_dev(unb_ctx *ctx, const double *unormed, const double *u,
                                              size_t n, size_t ndim, const uint8_t *selected,
                                              size_t nrounds, size_t round_lo, size_t round_hi,

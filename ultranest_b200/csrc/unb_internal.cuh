@@ -336,6 +336,9 @@ struct LiveUpdateArgs {
     double t32_r2, kappa32;
 };
 int unb_launch_live_update(unb_ctx *ctx, const LiveUpdateArgs &a, cudaStream_t s);
+int unb_launch_round_moments(unb_ctx *ctx, const double *u, int d, const int *idxA, const int *offA,
+                             const int *nA, int max_rows, int rounds, const double *c0, double *sums,
+                             double *sxx, cudaStream_t s);
 // clustered live tiles + binned proposals (unb_cluster.cu)
 size_t unb_cluster_max_tiles();
 int unb_launch_cluster_live(unb_ctx *ctx, const double *rows, int n, int d, int K, int *perm,

@@ -446,7 +446,85 @@ def _rewind_rounds(rng, state, npoints, rounds_consumed):
         rng.randint(npoints, size=npoints)
 
 
-def _bootstrap_rounds(u, unormed, selected, lo, hi, minvol):
+#: relative margin of the enlargement screen (see :func:`_bootstrap_rounds_screened`)
+SCREEN_MARGIN = 1e-6
+#: how often the screen was used / declined / how many rounds needed the exact host algebra
+screen_stats = {"screened": 0, "declined": 0, "exact_rounds": 0, "rounds": 0}
+
+
+def _bootstrap_rounds_screened(u, unormed, selected, lo, hi, active):
+    """The same per-round results as :func:`_bootstrap_rounds` with (almost) no host algebra.
+
+    ``compute_enlargement`` only needs ``max_r f_r`` (mlfriends.pyx:1062-1066).  So the per-round
+    bounding ellipsoids are first taken from moments accumulated ON THE DEVICE
+    (``unb_region_bootstrap_moments``: mean and covariance up to summation order; the 30 small
+    ``inv`` stay on the host as one batched LAPACK call), the device evaluates every round's ``f``
+    with them, and only the rounds whose screened ``f`` lies within ``SCREEN_MARGIN`` of the largest
+    are recomputed with the reference's own NumPy expressions (``np.cov``, ``inv``) -- typically
+    one round instead of thirty.  The maximum is then attained by an exactly computed round and
+    every other round is below it by more than the screen can err (covariances are required to be
+    well conditioned for that: ``cond * 1e-13 << SCREEN_MARGIN``), so the returned maximum is the
+    reference's value bit for bit.  Returns ``None`` whenever anything looks unusual (few points,
+    ill-conditioned or singular covariance, non-positive ``f``); the caller then runs the exact
+    path, which also reproduces the reference's failure semantics."""
+    eng = _engine()
+    nrounds, N = selected.shape
+    ndim = u.shape[1]
+    act = [r for r in range(lo, hi) if active[r]]
+    if len(act) < 3 or N < 8 * (ndim + 2):
+        return None
+    c0 = np.mean(u, axis=0)
+    counts, sums, sxx = eng.region_bootstrap_moments(u, selected, c0, lo, hi)
+    n = counts[act].astype(float)
+    if (n < 4 * (ndim + 2)).any():
+        return None
+    ybar = sums[act] / n[:, None]
+    S = sxx[act]
+    S = np.triu(S) + np.transpose(np.triu(S, 1), (0, 2, 1))
+    with np.errstate(all='ignore'):
+        cov = (S - n[:, None, None] * ybar[:, :, None] * ybar[:, None, :]) / (n - 1)[:, None, None] * (ndim + 2)
+        try:
+            inv = np.linalg.inv(cov)
+        except np.linalg.LinAlgError:
+            return None
+        if not (np.isfinite(cov).all() and np.isfinite(inv).all()):
+            return None
+        cond = np.sqrt((cov**2).sum(axis=(1, 2))) * np.sqrt((inv**2).sum(axis=(1, 2)))
+    if not cond.max() * 1e-13 < SCREEN_MARGIN * 1e-2:
+        return None
+    ctrs = np.zeros((nrounds, ndim))
+    invcovs = np.zeros((nrounds, ndim, ndim))
+    ctrs[act] = c0 + ybar
+    invcovs[act] = inv
+    maxd_r, f_r = eng.region_bootstrap(unormed, selected, u=u, ctrs=ctrs, invcovs=invcovs,
+                                       round_lo=lo, round_hi=hi)
+    fa = f_r[act]
+    if not (np.isfinite(fa).all() and (fa > 0).all()):
+        return None
+    cand = [r for r in act if f_r[r] >= fa.max() * (1.0 - SCREEN_MARGIN)]
+    for r in cand:      # the rounds that can decide the maximum: the reference's own algebra
+        try:
+            ctr, cov_r = bounding_ellipsoid(u[selected[r], :], minvol=0.)
+            invcovs[r] = np.linalg.inv(cov_r)
+            ctrs[r] = ctr
+        except (np.linalg.LinAlgError, FloatingPointError, AssertionError, Warning):
+            return None
+        _, f_exact = eng.region_bootstrap(None, selected, u=u, ctrs=ctrs, invcovs=invcovs,
+                                          round_lo=r, round_hi=r + 1)
+        if not (np.isfinite(f_exact[r]) and f_exact[r] > 0):
+            return None
+        f_r[r] = f_exact[r]
+    top = max(f_r[r] for r in cand)
+    rest = [f_r[r] for r in act if r not in cand]
+    if rest and not max(rest) < top * (1.0 - SCREEN_MARGIN / 2):
+        return None
+    screen_stats["screened"] += 1
+    screen_stats["exact_rounds"] += len(cand)
+    screen_stats["rounds"] += len(act)
+    return maxd_r, f_r, active, None
+
+
+def _bootstrap_rounds(u, unormed, selected, lo, hi, minvol, screen=True):
     """Rounds ``lo <= r < hi`` of the MLFriends bootstrap: per-round radius^2 (float32-rounded
     like the reference) and enlargement.  Host: d x d ``bounding_ellipsoid`` / ``inv`` of each
     round (mlfriends.pyx:1057-1058); device: everything O(N^2 d) / O(N d^2).
@@ -458,6 +536,11 @@ def _bootstrap_rounds(u, unormed, selected, lo, hi, minvol):
     nrounds, N = selected.shape
     ndim = u.shape[1]
     active = ~(selected.all(axis=1) | ~selected.any(axis=1))
+    if screen and minvol == 0:
+        out = _bootstrap_rounds_screened(u, unormed, selected, lo, hi, active)
+        if out is not None:
+            return out
+        screen_stats["declined"] += 1
     ctrs = np.zeros((nrounds, ndim))
     invcovs = np.zeros((nrounds, ndim, ndim))
     failure = None
