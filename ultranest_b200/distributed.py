@@ -161,8 +161,12 @@ def reduce_enlargement(u, unormed, selected, minvol=0., compute_rounds=None, mas
     proves it, a mismatch raises.  ``masks="broadcast"``: rank 0's masks are shipped first (a
     second collective) -- for callers whose ranks do not share a random stream.
 
-    On NCCL the per-round results never visit the host: the library folds them on the device
-    into the 5-double buffer that the collective reduces in place (``unb_region_bootstrap_fold_dev``).
+    On NCCL a rank's slice first goes through the enlargement screen
+    (``mlfriends._bootstrap_rounds_screened``: device moments, the reference's NumPy algebra only
+    for the rounds that can decide the maximum); when the screen does not apply (fewer than three
+    local rounds, few points, ``minvol``) the exact per-round algebra runs on the host and the
+    per-round results never leave the device: the library folds them into the 5-double buffer
+    that the collective reduces in place (``unb_region_bootstrap_fold_dev``).
     ``compute_rounds(u, unormed, selected, lo, hi, minvol) -> (maxd_r, f_r, active, failure)``
     replaces the device path (the CPU tests inject the oracle here; gloo has no device buffer).
     Any exception on one rank still reaches the collective (failed flag), so no rank is left
@@ -185,7 +189,21 @@ def reduce_enlargement(u, unormed, selected, minvol=0., compute_rounds=None, mas
     message = None
     buf = None
     try:
-        if on_device:
+        screened = None
+        if on_device and minvol == 0 and hi > lo:
+            # the enlargement screen (mlfriends._bootstrap_rounds_screened) applies to a rank's
+            # slice as well: the global maximum is some rank's local maximum, and that one is
+            # computed with the reference's exact algebra.  It needs the screened f on the host to
+            # pick its candidates, so this rank's three numbers travel to the device as 40 bytes.
+            from .mlfriends import _bootstrap_rounds_screened
+            active = ~(selected.all(axis=1) | ~selected.any(axis=1))
+            screened = _bootstrap_rounds_screened(u, unormed, selected, lo, hi, active)
+        if screened is not None:
+            maxd_r, f_r, active, _ = screened
+            rounds = [r for r in range(lo, hi) if active[r]]
+            buf = torch.tensor([max(maxd_r[r] for r in rounds), max(f_r[r] for r in rounds), 0.0,
+                                tag, -tag], dtype=torch.float64, device=dev)
+        elif on_device:
             from .mlfriends import _engine
             ctrs, invcovs, stop, failure = _host_rounds(u, selected, lo, hi, minvol)
             if failure is not None:
