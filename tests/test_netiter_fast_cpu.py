@@ -1,6 +1,6 @@
 """CPU: the fast MultiCounter (ultranest_b200.netiter) is the reference's
-MultiCounter: the same seeded run, every attribute after every node bit for bit, at a fraction
-of the time of `passing_node`."""
+MultiCounter -- its own `passing_node` running on a count-friendly `rootids` array: the same seeded
+run, every attribute after every node bit for bit, at a fraction of the time."""
 import time
 
 import numpy as np
@@ -86,17 +86,38 @@ def test_fast_multicounter_is_the_reference(random, check):
     print("passing_node: reference %.3fs fast %.3fs" % (t_ref, t_fast))
 
 
-def test_count_live_handles_duplicates_and_bad_ids():
+def test_lazy_column_count_handles_duplicates_bad_ids_and_other_uses():
     oracle.reference()
     from ultranest_b200 import netiter as fastmod
     fast_cls = fastmod.install()
     try:
         np.random.seed(1)
-        it = fast_cls(nroots=50, nbootstraps=7)
-        ids = np.array([3, 3, 3, 10, 49, 0, 0])
-        assert (it._count_live(ids) == it.rootids[:, ids].sum(axis=1)).all()
-        assert it._count_live(ids).dtype == it.rootids[:, ids].sum(axis=1).dtype
+        it = fast_cls(nroots=300, nbootstraps=7)
+        plain = np.array(it.rootids)                       # an ordinary copy of the masks
+        assert type(plain) is np.ndarray and plain.dtype == bool
+        rng = np.random.RandomState(2)
+        ids = rng.randint(300, size=500)                   # duplicates: arcs of the same root
+        got = it.rootids[:, ids].sum(axis=1)
+        want = plain[:, ids].sum(axis=1)
+        assert (got == want).all() and got.dtype == want.dtype
+        # every other use of the lazy object behaves like the gathered array
+        lazy = it.rootids[:, ids]
+        assert (np.asarray(lazy) == plain[:, ids]).all()
+        assert lazy.shape == plain[:, ids].shape and len(lazy) == len(plain)
+        assert (lazy.sum(axis=0) == plain[:, ids].sum(axis=0)).all()
+        assert lazy.sum() == plain[:, ids].sum()
+        assert (lazy[0] == plain[0, ids]).all()
+        # short index lists, scalar columns, row picks and negative ids take NumPy's own path
+        assert (it.rootids[:, ids[:5]] == plain[:, ids[:5]]).all()
+        assert (it.rootids[:, 3] == plain[:, 3]).all()
+        assert (it.rootids[0, ids] == plain[0, ids]).all()
+        neg = ids.copy()
+        neg[0] = -1
+        assert (it.rootids[:, neg].sum(axis=1) == plain[:, neg].sum(axis=1)).all()
+        bad = ids.copy()
+        bad[10] = 300
         with pytest.raises(IndexError):
-            it._count_live(np.array([1, 50]))
+            it.rootids[:, bad].sum(axis=1)
+        assert len(it.rootids) == 8
     finally:
         fastmod.uninstall()
