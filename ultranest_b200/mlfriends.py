@@ -15,6 +15,16 @@ the reference module, so ``ultranest/integrator.py`` runs unchanged on top of it
   (``region.u[i] = ...``, ``region.unormed[i] = ...``, ``region.ellipsoid_center = ...``,
   ``region.maxradiussq = None``; integrator.py:2749-2758, 2827).
 
+  These host pieces are NOT new work: ``make_eigvals_positive``, ``bounding_ellipsoid``,
+  ``vol_prefactor``, the layers' ``optimize`` / ``create_new``, ``create_ellipsoid`` / ``_set_axes``,
+  ``SimpleRegion.compute_enlargement``, ``WrappingEllipsoid`` and the friends-of-friends growth loop
+  are the reference's own NumPy expressions (mlfriends.pyx:275-322, 389-476, 547-569, 666-710,
+  754-816, 1213-1237, 1460-1649), kept expression for expression because a seeded run is only the
+  reference's run if these values are bit-identical -- roughly 250 of this file's lines.  What is new
+  lives in ``csrc/`` and in the orchestration around it here: the device mirror (``_bind``), the
+  fused calls, the bootstrap orchestration and its enlargement screen, the transform tolerance,
+  the device-side proposal generator.
+
 There is no CPU implementation of the scans in this package; without the CUDA library the
 import fails.
 """
