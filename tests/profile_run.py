@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""cProfile of one arm of tools/run_compare.py (default: the drop-in arm) -- where a whole
+"""cProfile of one arm of tests/run_compare.py (default: the drop-in arm) -- where a whole
 ReactiveNestedSampler run spends its time once the region is on the device.
 
-    python tools/profile_run.py [reference|ours|device]
+    python tests/profile_run.py [reference|ours|device]
 """
 import cProfile
 import io

@@ -6,7 +6,7 @@ behind the same names, (c) additionally the likelihood on the device and the fus
 Each arm runs in its own process; the runs must be the same run
 (niter, ncall, logZ), so the wall-clock ratio is the end-to-end effect of the drop-in.
 
-    python tools/run_compare.py [--ndim 20] [--nlive 4000] [--max-ncalls 8000]
+    python tests/run_compare.py [--ndim 20] [--nlive 4000] [--max-ncalls 8000]
 """
 import argparse
 import json

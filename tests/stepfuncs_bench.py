@@ -2,7 +2,7 @@
 """Population step-sampler helpers: reference (oracle/_ref, compiled Cython + NumPy callables on one
 host core) vs the device path, per call, for growing populations.
 
-    python tools/stepfuncs_bench.py [--d 20]
+    python tests/stepfuncs_bench.py [--d 20]
 """
 import argparse
 import json
